@@ -1,0 +1,13 @@
+import torch
+
+
+class ModelMixin(torch.nn.Module):
+    _supports_gradient_checkpointing = False
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
