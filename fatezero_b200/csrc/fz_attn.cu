@@ -1,0 +1,562 @@
+// fz_attn.cu — fused attention for the FateZero hot path (sm_100a: TMA + tcgen05 + TMEM).
+//
+// One kernel computes  O = f(softmax(scale * Q K^T)) V  for
+//   * the spatio-temporal self-attention (K/V of 0..n frames selected per query frame:
+//     prompt_attention/attention_register.py:131-218, models/attention.py:366-398), and
+//   * the text cross-attention (77 keys: attention_register.py:71-128),
+// with the controller hook of attention_register.py:49-51 fused INLINE (no probability tensor in HBM unless it is the cache):
+//   STORE      inversion: the fp16 probabilities are written once to the HBM map cache with TMA stores straight from the
+//              swizzled P tile that also feeds the PV MMA (attention_store.py:81-93), optional fp16 running sum (:95-101)
+//   REPLACE    edit, self-attention inside the replace window: P tile is TMA-loaded from the cache, QK^T/softmax skipped
+//              (attention_util.py:80-92 without mask)
+//   BLEND      edit, self-attention with a per-(frame,pixel) mask: rows with mask==0 take the cached row (:86-88)
+//   CROSSEDIT  edit, cross-attention: Refine gather / Replace 77x77 / Reweight / alpha-lerp in registers (:130-131,213-253,282-286)
+// Two passes over the keys (max[/sum] first, then probabilities): the normalised fp16 P the reference stores and multiplies is
+// reproduced exactly at its rounding point; rows that are neither stored nor edited use the cheaper "max only" first pass and
+// normalise O at the end.
+//
+// CTA = 128 query rows of one (frame, head); 6 warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue (1 row per thread).
+// TMEM: S double buffer (2 x 128 cols) + O (<= 192 cols).  smem: Q tile, a ring of K / V^T atoms, P double buffer (+ base P).
+#include "fz_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/fatezero_b200.h"
+
+namespace fz {
+
+constexpr int kMaxSlots = 4;
+constexpr int kMaxBF = 64;
+constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
+
+struct AttnParams {
+  CUtensorMap tmQ;      // (d, heads, S_q, BF)                 box (64, 1, 128, 1)
+  CUtensorMap tmK;      // (d, heads, keys_per_slot, SRC)      box (64, 1, 64, 1)
+  CUtensorMap tmVt;     // (keys_ld, d, heads, SRC)            box (64, d_pad, 1, 1)
+  CUtensorMap tmStore;  // (keys_ld_cache, slots, S_q, heads, Fc) box (64, 1, 128, 1, 1)   cache slab written (STORE)
+  CUtensorMap tmBase;   // same geometry, cache slab read (REPLACE / BLEND)
+  int S_q;              // queries per (frame, head)
+  int keys_per_slot;    // S for self-attention, 77 for cross
+  int n_slots;          // key/value frames per query frame (self: 1..4, cross: 1)
+  int d, d_pad, nd;     // head dim, padded to 16, number of 64-wide chunks
+  int heads, F, BF;
+  int ring_stages, ring_stage_bytes;
+  float scale_log2;     // scale * log2(e)
+  int src_index[kMaxSlots][kMaxBF];  // K/V source row (frame or text batch) per slot and query frame
+  // controller
+  int edit_bf_start;    // rows bf >= edit_bf_start get row_mode; cache frame = bf - edit_bf_start
+  int row_mode;         // FZ_ATTN_*
+  __half* acc;          // running sum [Fc, heads, S_q, acc_ld] fp16 or null (cross maps)
+  long long acc_ld;
+  const __half* base_rows;  // CROSSEDIT: cached source map [Fc, heads, S_q, base_ld]
+  long long base_ld;
+  const float* xedit;   // CROSSEDIT tables in device memory: see fz_cross_edit_t
+  const float* mask;    // BLEND: [Fc, S_q] 1 = keep current row, 0 = take cached row
+  __half* out;          // [BF*S_q, ldo], this head's columns start at head*d
+  long long ldo;
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct AtomInfo {
+  int slot, k0, valid;
+};
+__device__ __forceinline__ AtomInfo atom_info(const AttnParams& p, int atoms_per_slot, int A) {
+  AtomInfo a;
+  a.slot = A / atoms_per_slot;
+  a.k0 = (A % atoms_per_slot) * 64;
+  a.valid = min(64, p.keys_per_slot - a.k0);
+  return a;
+}
+
+__global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int bf = blockIdx.z;
+  const bool edited = bf >= p.edit_bf_start && p.row_mode != FZ_ATTN_NONE;
+  const int row_mode = edited ? p.row_mode : FZ_ATTN_NONE;
+  const int fc = bf - p.edit_bf_start;
+  const bool replace = row_mode == FZ_ATTN_REPLACE;
+  const bool blend = row_mode == FZ_ATTN_BLEND;
+  const bool exact = row_mode != FZ_ATTN_NONE;  // pass 1 accumulates the sum, pass 2 emits normalised probabilities
+
+  uint8_t* s_q = smem;
+  uint8_t* s_ring = s_q + p.nd * kAtomBytes;
+  uint8_t* s_p = s_ring + p.ring_stages * p.ring_stage_bytes;
+  uint8_t* s_pbase = s_p + 2 * 2 * kAtomBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pbase + (p.row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0));
+  uint64_t* ring_full = bars;
+  uint64_t* ring_empty = bars + 8;
+  uint64_t* q_full = bars + 16;
+  uint64_t* s_full = bars + 17;   // [2]
+  uint64_t* s_empty = bars + 19;  // [2]
+  uint64_t* p_full = bars + 21;   // [2]
+  uint64_t* p_empty = bars + 23;  // [2]
+  uint64_t* o_full = bars + 25;
+  uint64_t* base_full = bars + 26;
+  uint64_t* base_empty = bars + 27;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int atoms_per_slot = (p.keys_per_slot + 63) / 64;
+  const int n_atoms = atoms_per_slot * p.n_slots;
+  const int n_blocks = (n_atoms + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmVt);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&ring_full[s], 1);
+      mbar_init(&ring_empty[s], 1);
+    }
+    mbar_init(q_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 4);
+      mbar_init(&p_full[b], 1);
+      mbar_init(&p_empty[b], 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(base_full, 1);
+    mbar_init(base_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
+      auto load_k_block = [&](int b) {
+        const int na = min(2, n_atoms - 2 * b);
+        for (int c = 0; c < p.nd; ++c) {
+          mbar_wait(&ring_empty[stage], phase ^ 1);
+          uint8_t* dst = s_ring + stage * p.ring_stage_bytes;
+          mbar_expect_tx(&ring_full[stage], na * 64 * 128);
+          for (int a = 0; a < na; ++a) {
+            const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
+            tma_load_4d(dst + a * 64 * 128, &p.tmK, &ring_full[stage], c * 64, head, ai.k0, p.src_index[ai.slot][bf]);
+          }
+          advance();
+        }
+      };
+      auto load_v_block = [&](int b) {
+        const int na = min(2, n_atoms - 2 * b);
+        for (int a = 0; a < na; ++a) {
+          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
+          mbar_wait(&ring_empty[stage], phase ^ 1);
+          mbar_expect_tx(&ring_full[stage], p.d_pad * 128);
+          tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmVt, &ring_full[stage], ai.k0, 0, head, p.src_index[ai.slot][bf]);
+          advance();
+        }
+      };
+      auto load_base_block = [&](int b, uint8_t* dst, uint64_t* bar) {
+        const int na = min(2, n_atoms - 2 * b);
+        mbar_expect_tx(bar, na * kAtomBytes);
+        for (int a = 0; a < na; ++a) {
+          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
+          tma_load_5d(dst + a * kAtomBytes, &p.tmBase, bar, ai.k0, ai.slot, q0, head, fc);
+        }
+      };
+      if (!replace) {
+        // Q tile: nd atoms of [128 rows x 64 dims]
+        mbar_expect_tx(q_full, p.nd * kAtomBytes);
+        for (int c = 0; c < p.nd; ++c) tma_load_4d(s_q + c * kAtomBytes, &p.tmQ, q_full, c * 64, head, q0, bf);
+        for (int b = 0; b < n_blocks; ++b) load_k_block(b);  // pass 1
+        load_k_block(0);                                      // pass 2
+        for (int b = 0; b < n_blocks; ++b) {
+          if (b + 1 < n_blocks) load_k_block(b + 1);
+          if (blend) {
+            mbar_wait(base_empty, ((b & 1) ^ 1));
+            load_base_block(b, s_pbase, base_full);
+          }
+          load_v_block(b);
+        }
+      } else {
+        for (int b = 0; b < n_blocks; ++b) {
+          const int pb = b & 1;
+          mbar_wait(&p_empty[pb], ((b >> 1) & 1) ^ 1);
+          load_base_block(b, s_p + pb * 2 * kAtomBytes, &p_full[pb]);
+          load_v_block(b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================== MMA issuer ===========================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
+      const uint32_t idesc_o = umma_idesc_f16(128, p.d_pad);
+      int g = 0;  // S-buffer use counter across both passes
+      auto issue_s = [&](int b) {
+        const int buf = g & 1;
+        mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const int na = min(2, n_atoms - 2 * b);
+        const uint32_t idesc_s = umma_idesc_f16(128, na * 64);
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (int c = 0; c < p.nd; ++c) {
+          mbar_wait(&ring_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s_q + c * kAtomBytes);
+          const uint32_t sb = smem_u32(s_ring + stage * p.ring_stage_bytes);
+          const int ksteps = min(4, (p.d - c * 64 + 15) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc_s, (c | k) ? 1u : 0u);
+          umma_commit(&ring_empty[stage]);
+          advance();
+        }
+        umma_commit(&s_full[buf]);
+        ++g;
+      };
+      auto issue_pv = [&](int b) {
+        const int pb = b & 1;
+        mbar_wait(&p_full[pb], (b >> 1) & 1);
+        tc_fence_after();
+        const int na = min(2, n_atoms - 2 * b);
+        for (int a = 0; a < na; ++a) {
+          mbar_wait(&ring_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s_p + pb * 2 * kAtomBytes + a * kAtomBytes);
+          const uint32_t sb = smem_u32(s_ring + stage * p.ring_stage_bytes);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_o, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc_o, (b | a | k) ? 1u : 0u);
+          umma_commit(&ring_empty[stage]);
+          advance();
+        }
+        umma_commit(&p_empty[pb]);
+      };
+      if (!replace) {
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        for (int b = 0; b < n_blocks; ++b) issue_s(b);
+        issue_s(0);
+        for (int b = 0; b < n_blocks; ++b) {
+          if (b + 1 < n_blocks) issue_s(b + 1);
+          issue_pv(b);
+        }
+      } else {
+        for (int b = 0; b < n_blocks; ++b) issue_pv(b);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // =========================================== softmax / epilogue warps ===========================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const int q = q0 + row;
+    const bool row_ok = q < p.S_q;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const int st = threadIdx.x - 64;  // 0..127 among the softmax threads
+    float m_run = -INFINITY, l_run = 0.f;
+    int g = 0;
+    if (!replace) {
+      // ------------------------------ pass 1: row max (and sum when exact) ------------------------------
+      for (int b = 0; b < n_blocks; ++b, ++g) {
+        const int buf = g & 1;
+        mbar_wait(&s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        const int na = min(2, n_atoms - 2 * b);
+        for (int a = 0; a < na; ++a) {
+          const int valid = atom_info(p, atoms_per_slot, 2 * b + a).valid;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + c, r);
+            tmem_ld_wait();
+            float cm = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float s = (c + e < valid) ? __uint_as_float(r[e]) * p.scale_log2 : -INFINITY;
+              r[e] = __float_as_uint(s);
+              cm = fmaxf(cm, s);
+            }
+            if (exact) {
+              const float m_new = fmaxf(m_run, cm);
+              if (m_new > -INFINITY) {
+                float acc = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc += ex2(__uint_as_float(r[e]) - m_new);
+                l_run = l_run * ex2(m_run - m_new) + acc;
+              }
+              m_run = m_new;
+            } else {
+              m_run = fmaxf(m_run, cm);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+      }
+      const float inv_l = exact ? (1.0f / l_run) : 1.0f;
+      float l_fast = 0.f;
+      const float mrow = blend ? p.mask[static_cast<long long>(fc) * p.S_q + min(q, p.S_q - 1)] : 1.f;
+      const float* xe = p.xedit;
+      // ------------------------------ pass 2: probabilities -> P tile (-> cache) ------------------------------
+      for (int b = 0; b < n_blocks; ++b, ++g) {
+        const int buf = g & 1, pb = b & 1;
+        mbar_wait(&s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<1>();  // P buffer pb was read by the store issued 2 blocks ago
+        mbar_wait(&p_empty[pb], ((b >> 1) & 1) ^ 1);
+        named_bar_sync(1, 128);
+        if (blend) { mbar_wait(base_full, b & 1); }
+        uint8_t* pbuf = s_p + pb * 2 * kAtomBytes;
+        const int na = min(2, n_atoms - 2 * b);
+        for (int a = 0; a < na; ++a) {
+          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
+          uint8_t* prow = pbuf + a * kAtomBytes + row * 128;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + c, r);
+            tmem_ld_wait();
+            float pv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float s = (c + e < ai.valid) ? __uint_as_float(r[e]) * p.scale_log2 : -INFINITY;
+              pv[e] = ex2(s - m_run) * inv_l;
+            }
+            if (!exact) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) l_fast += pv[e];
+            }
+            if (row_mode == FZ_ATTN_CROSSEDIT || (p.acc && edited)) {
+              // key index n = ai.k0 + c + e (single slot).  cur = fp16(p); optional running sum; optional edit (in fp32, one rounding)
+              const int n0 = ai.k0 + c;
+              const long long rbase = ((static_cast<long long>(fc) * p.heads + head) * p.S_q + min(q, p.S_q - 1));
+              if (p.acc && row_ok) {
+                __half* ap = p.acc + rbase * p.acc_ld + n0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                  if (n0 + e < p.acc_ld) {
+                    uint4 v = *reinterpret_cast<uint4*>(ap + e);
+                    __half* hv = reinterpret_cast<__half*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(__half2float(hv[j]) + __half2float(__float2half_rn(pv[e + j])));
+                    *reinterpret_cast<uint4*>(ap + e) = v;
+                  }
+                }
+              }
+              if (row_mode == FZ_ATTN_CROSSEDIT) {
+                const __half* brow = p.base_rows + rbase * p.base_ld;
+                const int xmode = static_cast<int>(xe[0]);  // 0 refine, 1 replace
+                const float* x_alpha = xe + 8;              // [80] cross_replace_alpha of this step
+                const float* x_eq = xe + 8 + 80;            // [80] equalizer (1 when absent)
+                const float* x_a = xe + 8 + 160;            // [80] refine alphas
+                const float* x_map = xe + 8 + 240;          // [80] refine mapper (as float)
+                const float* x_M = xe + 8 + 320;            // [80][80] replace matrix M[w][n]
+                float rr[32];
+                if (xmode == 1) {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) rr[e] = 0.f;
+                  for (int w = 0; w < p.keys_per_slot; ++w) {
+                    const float bw = __half2float(brow[w]);
+                    const float* mrow_p = x_M + w * 80 + n0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                      if (n0 + e < 80) rr[e] += bw * __ldg(mrow_p + e);
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const int n = n0 + e;
+                  if (n < p.keys_per_slot) {
+                    const float cur = __half2float(__float2half_rn(pv[e]));
+                    float R;
+                    if (xmode == 1) R = rr[e];
+                    else {
+                      int mi = static_cast<int>(__ldg(x_map + n));
+                      if (mi < 0) mi += p.keys_per_slot;  // python negative index (masked by a[n] == 0)
+                      const float an = __ldg(x_a + n);
+                      R = __half2float(brow[mi]) * an + cur * (1.f - an);
+                    }
+                    R *= __ldg(x_eq + n);
+                    const float al = __ldg(x_alpha + n);
+                    pv[e] = R * al + (1.f - al) * cur;
+                  }
+                }
+              }
+            }
+            // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 v;
+              v.x = pack_half2(pv[e + 0], pv[e + 1]);
+              v.y = pack_half2(pv[e + 2], pv[e + 3]);
+              v.z = pack_half2(pv[e + 4], pv[e + 5]);
+              v.w = pack_half2(pv[e + 6], pv[e + 7]);
+              const int j = (c + e) >> 3;
+              *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
+            }
+          }
+          if (blend) {
+            if (mrow == 0.f) {
+              const uint8_t* srow = s_pbase + a * kAtomBytes + row * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(prow + j * 16) = *reinterpret_cast<const uint4*>(srow + j * 16);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[buf]);
+          if (blend) mbar_arrive(base_empty);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (st == 0) {
+          if (row_mode == FZ_ATTN_STORE) {
+            for (int a = 0; a < na; ++a) {
+              const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
+              tma_store_5d(&p.tmStore, pbuf + a * kAtomBytes, ai.k0, ai.slot, q0, head, fc);
+            }
+            tma_store_commit();
+          }
+          mbar_arrive(&p_full[pb]);
+        }
+      }
+      if (!exact) l_run = l_fast;
+    }
+    // ------------------------------ epilogue: O (TMEM) -> fp16 -> global ------------------------------
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float o_scale = (!replace && !exact) ? (1.0f / l_run) : 1.0f;
+    __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + min(q, p.S_q - 1)) * p.ldo + head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < p.d_pad; c += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_o + lane_addr + c, r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 8) {
+          if (c + e < p.d) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(r[e + 0]) * o_scale, __uint_as_float(r[e + 1]) * o_scale);
+            v.y = pack_half2(__uint_as_float(r[e + 2]) * o_scale, __uint_as_float(r[e + 3]) * o_scale);
+            v.z = pack_half2(__uint_as_float(r[e + 4]) * o_scale, __uint_as_float(r[e + 5]) * o_scale);
+            v.w = pack_half2(__uint_as_float(r[e + 6]) * o_scale, __uint_as_float(r[e + 7]) * o_scale);
+            *reinterpret_cast<uint4*>(orow + c + e) = v;
+          }
+        }
+      }
+    }
+    if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace fz
+
+using namespace fz;
+
+static int encode_cache_map(CUtensorMap* tm, const void* base, int keys_ld_slot, int n_slots, int S_q, int heads, int Fc, long long row_ld) {
+  // cache slab [Fc, heads, S_q, row_ld] fp16; a row holds n_slots runs of keys_ld_slot keys (self) or one run (cross)
+  uint64_t dims[5] = {(uint64_t)keys_ld_slot, (uint64_t)n_slots, (uint64_t)S_q, (uint64_t)heads, (uint64_t)Fc};
+  uint64_t strides[4] = {(uint64_t)keys_ld_slot, (uint64_t)row_ld, (uint64_t)row_ld * S_q, (uint64_t)row_ld * S_q * heads};
+  uint32_t box[5] = {64, 1, 128, 1, 1};
+  return encode_tmap_f16(tm, base, 5, dims, strides, box, true);
+}
+
+extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
+  FZ_CHECK_ARG(a && a->q && a->k && a->vt && a->out, "fz_attention: null pointer");
+  FZ_CHECK_ARG(a->d % 8 == 0 && a->d >= 8 && a->d <= 192, "fz_attention: head dim %d unsupported", a->d);
+  FZ_CHECK_ARG(a->n_slots >= 1 && a->n_slots <= kMaxSlots && a->BF <= kMaxBF, "fz_attention: n_slots=%d BF=%d unsupported", a->n_slots, a->BF);
+  FZ_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->vt_ld % 8 == 0 && a->ldo % 8 == 0, "fz_attention: leading dims must be multiples of 8");
+  FZ_CHECK_ARG(a->keys_per_slot >= 1 && a->keys_per_slot <= a->vt_ld, "fz_attention: keys_per_slot > vt_ld");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.S_q = a->S_q; p.keys_per_slot = a->keys_per_slot; p.n_slots = a->n_slots;
+  p.d = a->d; p.d_pad = (a->d + 15) / 16 * 16; p.nd = (a->d + 63) / 64;
+  p.heads = a->heads; p.F = a->F; p.BF = a->BF;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  for (int s = 0; s < a->n_slots; ++s)
+    for (int i = 0; i < a->BF; ++i) p.src_index[s][i] = a->src_index[s * a->BF + i];
+  p.edit_bf_start = a->edit_bf_start; p.row_mode = a->row_mode;
+  p.acc = static_cast<__half*>(a->acc); p.acc_ld = a->acc_ld;
+  p.base_rows = static_cast<const __half*>(a->base); p.base_ld = a->cache_ld;
+  p.xedit = a->xedit; p.mask = a->mask;
+  p.out = static_cast<__half*>(a->out); p.ldo = a->ldo;
+  const int Fc = a->BF - a->edit_bf_start;
+  if (a->row_mode == FZ_ATTN_STORE) FZ_CHECK_ARG(a->store, "fz_attention: STORE needs a cache slab");
+  if (a->row_mode == FZ_ATTN_REPLACE || a->row_mode == FZ_ATTN_BLEND || a->row_mode == FZ_ATTN_CROSSEDIT)
+    FZ_CHECK_ARG(a->base, "fz_attention: REPLACE/BLEND/CROSSEDIT need the cached source map");
+  if (a->row_mode == FZ_ATTN_BLEND) FZ_CHECK_ARG(a->mask, "fz_attention: BLEND needs a mask");
+  if (a->row_mode == FZ_ATTN_CROSSEDIT) FZ_CHECK_ARG(a->xedit && a->n_slots == 1 && a->keys_per_slot <= 80, "fz_attention: CROSSEDIT needs tables, one slot, <= 80 keys");
+  if (a->acc) FZ_CHECK_ARG(a->n_slots == 1 && a->acc_ld % 8 == 0, "fz_attention: running sum only for single-slot maps");
+  {
+    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->S_q, (uint64_t)a->BF};
+    uint64_t strides[3] = {(uint64_t)a->d, (uint64_t)a->ldq, (uint64_t)a->ldq * a->S_q};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (int rc = encode_tmap_f16(&p.tmQ, a->q, 4, dims, strides, box, true)) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->keys_per_slot, (uint64_t)a->n_src};
+    uint64_t strides[3] = {(uint64_t)a->d, (uint64_t)a->ldk, (uint64_t)a->ldk * a->keys_per_slot};
+    uint32_t box[4] = {64, 1, 64, 1};
+    if (int rc = encode_tmap_f16(&p.tmK, a->k, 4, dims, strides, box, true)) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->keys_per_slot, (uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->n_src};
+    uint64_t strides[3] = {(uint64_t)a->vt_ld, (uint64_t)a->vt_ld * a->d, (uint64_t)a->vt_ld * a->d * a->heads};
+    uint32_t box[4] = {64, (uint32_t)p.d_pad, 1, 1};
+    if (int rc = encode_tmap_f16(&p.tmVt, a->vt, 4, dims, strides, box, true)) return rc;
+  }
+  // cache geometry: a row of the slab is n_slots * keys_ld_slot wide, keys_ld_slot = cache_ld / n_slots
+  if (a->store) {
+    if (int rc = encode_cache_map(&p.tmStore, a->store, (int)(a->cache_ld / a->n_slots), a->n_slots, a->S_q, a->heads, Fc, a->cache_ld)) return rc;
+  } else {
+    p.tmStore = p.tmQ;
+  }
+  if (a->base && a->row_mode != FZ_ATTN_CROSSEDIT) {
+    if (int rc = encode_cache_map(&p.tmBase, a->base, (int)(a->cache_ld / a->n_slots), a->n_slots, a->S_q, a->heads, Fc, a->cache_ld)) return rc;
+  } else {
+    p.tmBase = p.tmQ;
+  }
+  // shared memory plan
+  const int stage_bytes = std::max(kAtomBytes, (p.d_pad * 128 + 1023) / 1024 * 1024);
+  const int fixed = p.nd * kAtomBytes + 4 * kAtomBytes + (a->row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0) + 1024 + 512;
+  int stages = 6;
+  while (stages > 2 && fixed + stages * stage_bytes > 225 * 1024) --stages;
+  FZ_CHECK_ARG(fixed + stages * stage_bytes <= 227 * 1024, "fz_attention: shared memory plan does not fit (d=%d)", a->d);
+  p.ring_stages = stages; p.ring_stage_bytes = stage_bytes;
+  const int smem = fixed + stages * stage_bytes;
+  static int configured = 0;
+  if (smem > configured) {
+    FZ_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid((a->S_q + 127) / 128, a->heads, a->BF);
+  attn_kernel<<<grid, 192, smem, stream>>>(p);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}

@@ -1,0 +1,508 @@
+// fz_gemm.cu — the "tap-GEMM": one persistent, warp-specialised tcgen05 kernel that serves every dense contraction of the
+// UNet step except attention:
+//     D[M, N] = sum_{tap} A_tap[M, K] * W_tap[N, K]^T   (+ bias, + per-batch time-embedding row, + residual, GEGLU, V^T store)
+//   * nn.Linear / 1x1 conv ............ 1 tap, A = [M, K] row-major tokens
+//   * 3x3 conv (stride 1 / stride 2) .. 9 taps, A = NHWC activation addressed through a 4-D / 5-D TMA map; the tap moves the
+//                                       box by (dy, dx) and TMA zero-fills the halo (implicit GEMM, no im2col in HBM)
+//   * temporal LoRA Conv1d(k=3) ....... 3 taps along the frame axis of [B, F, HW, C]
+// Reference ops replaced: models/resnet.py:57-80 (PseudoConv3d.forward), models/lora.py:46-54, nn.Linear call sites of
+// prompt_attention/attention_register.py:81,99-100,124,156-160,214 and diffusers FeedForward/GEGLU (models/attention.py:320).
+//
+// Structure (per CTA, 192 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0 : TMA producer   — A box {64ch, rows} + W box {64ch, BLOCK_N} per stage, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16  M=128 x N=BLOCK_N x K=16, fp32 accumulators in TMEM,
+//                             double-buffered accumulators (2 x BLOCK_N columns) so the epilogue overlaps the next tile
+//   warps 2-5 : epilogue    — tcgen05.ld 32x32b -> registers -> fused epilogue -> 16-byte global stores
+#include "fz_common.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fatezero_b200.h"
+
+namespace fz {
+
+constexpr int kMaxTaps = 9;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+
+struct TapGemmParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int a_rank;         // 2..5
+  int M, N;           // valid output rows / columns (for GEGLU: N = number of OUTPUT columns = half the GEMM columns)
+  int rows_per_tile;  // <= 128; tile t covers output rows [t*rows_per_tile, ...)
+  int a_box_bytes;    // bytes TMA writes for one A box (rows_per_tile * 128)
+  int k_blocks;       // per tap
+  int num_taps;
+  int n_tiles, m_tiles;
+  int ndecomp;        // how many of A's dims 1.. take part in the row decomposition
+  int dimsz[4];       // their sizes
+  int tap_off[kMaxTaps][5];  // coordinate offsets per tap for A dims 0..4
+  const float* bias;         // [gemm columns] fp32 (GEGLU: packed like the weights) or null
+  const float* group_bias;   // [M / rows_per_group, N] fp32 or null (time-embedding projection per batch element)
+  int rows_per_group;
+  const __half* residual;    // [M, ldr] or null
+  long long ldr;
+  __half* out;
+  long long ldo;
+  int mode;          // FZ_EPI_ROWMAJOR / FZ_EPI_GEGLU
+  int vt_col_start;  // gemm columns >= this are written transposed (V^T) instead of row-major; INT_MAX = off
+  __half* out_vt;    // [BF, heads, d, S]
+  int vt_S, vt_d, vt_heads, vt_ld;
+};
+
+template <int BLOCK_N>
+struct TapGemmCfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBTilePad = (kBTileBytes + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kATileBytes + kBTilePad;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  using Cfg = TapGemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.num_taps * p.k_blocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        int rem = mt * p.rows_per_tile;
+        int base[5] = {0, 0, 0, 0, 0};
+        for (int d = 0; d < p.ndecomp; ++d) {
+          base[d + 1] = rem % p.dimsz[d];
+          rem /= p.dimsz[d];
+        }
+        const int n0 = nt * BLOCK_N;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int c1 = base[1] + p.tap_off[tap][1], c2 = base[2] + p.tap_off[tap][2];
+          const int c3 = base[3] + p.tap_off[tap][3], c4 = base[4] + p.tap_off[tap][4];
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kATileBytes;
+            mbar_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBTileBytes);
+            const int c0 = kb * kBlockK + p.tap_off[tap][0];
+            switch (p.a_rank) {
+              case 2: tma_load_2d(sa, &p.tmA, &full[stage], c0, c1); break;
+              case 3: tma_load_3d(sa, &p.tmA, &full[stage], c0, c1, c2); break;
+              case 4: tma_load_4d(sa, &p.tmA, &full[stage], c0, c1, c2, c3); break;
+              default: tma_load_5d(sa, &p.tmA, &full[stage], c0, c1, c2, c3, c4); break;
+            }
+            tma_load_3d(sb, &p.tmB, &full[stage], kb * kBlockK, n0, tap);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t use = static_cast<uint32_t>(local >> 1);
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t use = static_cast<uint32_t>(local >> 1);
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const long long m = static_cast<long long>(mt) * p.rows_per_tile + row_in_tile;
+      const bool row_ok = row_in_tile < p.rows_per_tile && m < p.M;
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BLOCK_N;
+      if (p.mode == FZ_EPI_GEGLU) {
+        constexpr int HALF = BLOCK_N / 2;
+        constexpr int CH = (HALF >= 32) ? 32 : 16;
+        if constexpr (HALF >= 16) {
+#pragma unroll 1
+          for (int c = 0; c < HALF; c += CH) {
+            uint32_t xa[CH], ga[CH];
+            if constexpr (CH == 32) {
+              tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(xa));
+              tmem_ld_32x32b_x32(t_row + HALF + c, reinterpret_cast<uint32_t(&)[32]>(ga));
+            } else {
+              tmem_ld_32x32b_x16(t_row + c, reinterpret_cast<uint32_t(&)[16]>(xa));
+              tmem_ld_32x32b_x16(t_row + HALF + c, reinterpret_cast<uint32_t(&)[16]>(ga));
+            }
+            tmem_ld_wait();
+            const int ocol0 = nt * HALF + c;
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                __align__(16) __half hv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float xv = __uint_as_float(xa[j + e]), gv = __uint_as_float(ga[j + e]);
+                  if (p.bias) {
+                    xv += p.bias[nt * BLOCK_N + c + j + e];
+                    gv += p.bias[nt * BLOCK_N + HALF + c + j + e];
+                  }
+                  hv[e] = __float2half_rn(xv * gelu_erf(gv));
+                }
+                const int oc = ocol0 + j;
+                if (oc + 8 <= p.N) {
+                  *reinterpret_cast<uint4*>(p.out + m * p.ldo + oc) = *reinterpret_cast<const uint4*>(hv);
+                } else {
+                  for (int e = 0; e < 8; ++e)
+                    if (oc + e < p.N) p.out[m * p.ldo + oc + e] = hv[e];
+                }
+              }
+            }
+          }
+        }
+      } else {
+        constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += CH) {
+          uint32_t acc[CH];
+          if constexpr (CH == 32) tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(acc));
+          else tmem_ld_32x32b_x16(t_row + c, reinterpret_cast<uint32_t(&)[16]>(acc));
+          tmem_ld_wait();
+          const int col0 = nt * BLOCK_N + c;
+          if (row_ok && col0 < p.N) {
+            const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
+            if (col0 >= p.vt_col_start) {
+              // V^T store: out_vt[((bf*heads + h)*d + dd)*S + s]; lanes = consecutive s -> 64-byte coalesced segments
+              const long long bf = m / p.vt_S;
+              const int s = static_cast<int>(m % p.vt_S);
+#pragma unroll
+              for (int e = 0; e < CH; ++e) {
+                const int col = col0 + e;
+                if (col < p.N) {
+                  float v = __uint_as_float(acc[e]);
+                  if (p.bias) v += p.bias[col];
+                  const int cv = col - p.vt_col_start;
+                  const int h = cv / p.vt_d, dd = cv % p.vt_d;
+                  p.out_vt[((bf * p.vt_heads + h) * p.vt_d + dd) * p.vt_ld + s] = __float2half_rn(v);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                const int col = col0 + j;
+                if (col < p.N) {
+                  __align__(16) __half hv[8];
+                  __align__(16) __half rv[8];
+                  const bool full8 = col + 8 <= p.N;
+                  if (p.residual) {
+                    if (full8) *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col);
+                    else
+                      for (int e = 0; e < 8; ++e) rv[e] = (col + e < p.N) ? p.residual[m * p.ldr + col + e] : __half(0.f);
+                  }
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    float v = __uint_as_float(acc[j + e]);
+                    if (col + e < p.N) {
+                      if (p.bias) v += p.bias[col + e];
+                      if (gb) v += gb[col + e];
+                      if (p.residual) v += __half2float(rv[e]);
+                    }
+                    hv[e] = __float2half_rn(v);
+                  }
+                  if (full8) {
+                    *reinterpret_cast<uint4*>(p.out + m * p.ldo + col) = *reinterpret_cast<const uint4*>(hv);
+                  } else {
+                    for (int e = 0; e < 8; ++e)
+                      if (col + e < p.N) p.out[m * p.ldo + col + e] = hv[e];
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  using Cfg = TapGemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    FZ_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = std::min(tiles, num_sms());
+  tapgemm_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(p);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}
+
+static int pick_block_n(int gemm_cols, int mode, int forced) {
+  if (forced > 0) return forced;
+  static const int cands[] = {256, 160, 128, 64, 32, 16};
+  if (mode == FZ_EPI_GEGLU) return (gemm_cols % 256 == 0) ? 256 : ((gemm_cols % 160 == 0) ? 160 : ((gemm_cols % 128 == 0) ? 128 : ((gemm_cols % 64 == 0) ? 64 : 32)));
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int tiles = (gemm_cols + bn - 1) / bn;
+    // cost ~ MMA columns issued, with a mild penalty for narrow tiles (more A re-reads, more smem traffic per flop)
+    const double cost = static_cast<double>(tiles) * bn * (1.0 + 24.0 / bn);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cudaStream_t stream) {
+  const int bn = pick_block_n(gemm_cols, p.mode, forced_bn);
+  p.n_tiles = (gemm_cols + bn - 1) / bn;
+  switch (bn) {
+    case 256: return launch_tapgemm<256>(p, stream);
+    case 160: return launch_tapgemm<160>(p, stream);
+    case 128: return launch_tapgemm<128>(p, stream);
+    case 64: return launch_tapgemm<64>(p, stream);
+    case 32: return launch_tapgemm<32>(p, stream);
+    case 16: return launch_tapgemm<16>(p, stream);
+    default: set_error("unsupported BLOCK_N %d", bn); return FZ_ERR_INVALID;
+  }
+}
+
+static int fill_epilogue(TapGemmParams& p, const fz_epilogue_t* e, int M, int gemm_cols) {
+  p.bias = nullptr; p.group_bias = nullptr; p.rows_per_group = 1; p.residual = nullptr; p.ldr = 0;
+  p.mode = FZ_EPI_ROWMAJOR; p.vt_col_start = INT_MAX; p.out_vt = nullptr; p.vt_S = p.vt_d = p.vt_heads = p.vt_ld = 1;
+  p.N = gemm_cols;
+  if (!e) return FZ_OK;
+  p.bias = e->bias; p.group_bias = e->group_bias; p.rows_per_group = e->rows_per_group > 0 ? e->rows_per_group : 1;
+  p.residual = static_cast<const __half*>(e->residual); p.ldr = e->ldr;
+  p.mode = e->mode;
+  if (e->mode == FZ_EPI_GEGLU) {
+    FZ_CHECK_ARG(gemm_cols % 2 == 0, "GEGLU needs an even number of GEMM columns");
+    p.N = gemm_cols / 2;
+  }
+  if (e->out_vt) {
+    FZ_CHECK_ARG(e->vt_S > 0 && e->vt_d > 0 && e->vt_heads > 0 && M % e->vt_S == 0, "bad V^T geometry");
+    p.vt_col_start = e->vt_col_start; p.out_vt = static_cast<__half*>(e->out_vt);
+    p.vt_S = e->vt_S; p.vt_d = e->vt_d; p.vt_heads = e->vt_heads; p.vt_ld = e->vt_ld > 0 ? e->vt_ld : e->vt_S;
+  }
+  return FZ_OK;
+}
+
+}  // namespace fz
+
+using namespace fz;
+
+// D[M,N] = A[M,K] * W[N,K]^T (+epilogue).  A, W fp16 row-major (lda, ldw in elements, multiples of 8).
+extern "C" int fz_gemm_f16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const fz_epilogue_t* epi,
+                           void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  FZ_CHECK_ARG(A && W && out, "fz_gemm_f16: null pointer");
+  FZ_CHECK_ARG(M > 0 && N > 0 && K > 0, "fz_gemm_f16: bad shape %d %d %d", M, N, K);
+  FZ_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && K % 8 == 0, "fz_gemm_f16: lda/ldw/K must be multiples of 8 (16-byte TMA strides)");
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda)};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (int rc = encode_tmap_f16(&p.tmA, A, 2, dims, strides, box, true)) return rc;
+  }
+  const int rc0 = fill_epilogue(p, epi, M, N);
+  if (rc0) return rc0;
+  const int bn = pick_block_n(N, p.mode, force_block_n);
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 1};
+    uint64_t strides[2] = {static_cast<uint64_t>(ldw), static_cast<uint64_t>(ldw) * N};
+    uint32_t box[3] = {kBlockK, static_cast<uint32_t>(bn), 1};
+    if (int rc = encode_tmap_f16(&p.tmB, W, 3, dims, strides, box, true)) return rc;
+  }
+  p.a_rank = 2; p.M = M; p.rows_per_tile = kBlockM; p.a_box_bytes = kATileBytes;
+  p.k_blocks = (K + kBlockK - 1) / kBlockK; p.num_taps = 1;
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.ndecomp = 1; p.dimsz[0] = INT_MAX;
+  p.out = static_cast<__half*>(out); p.ldo = ldo;
+  return dispatch_tapgemm(p, N, bn, stream);
+}
+
+// 3x3 convolution, padding 1, stride 1 or 2, NHWC fp16.  x: [NB, H, W, Cin] (pixel stride ldx >= Cin),
+// w: [9][Cout][Cin] (tap-major, tap = ky*3+kx), out: [NB, Ho, Wo, Cout] row-major with row stride ldo.
+extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout, int stride,
+                                   const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && w && out, "fz_conv3x3: null pointer");
+  FZ_CHECK_ARG(stride == 1 || stride == 2, "fz_conv3x3: stride must be 1 or 2");
+  FZ_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "fz_conv3x3: Cin/ldx must be multiples of 8");
+  FZ_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "fz_conv3x3: stride 2 needs even H, W");
+  const int Ho = H / stride, Wo = W / stride;
+  FZ_CHECK_ARG(Wo <= 128, "fz_conv3x3: output width %d > 128 not supported", Wo);
+  // box over (x, y, n): full output width, as many rows / images as fit 128 GEMM rows
+  int bw = Wo, bh = std::min(Ho, 128 / bw);
+  while (Ho % bh) --bh;
+  int bn_img = (bh == Ho) ? std::min(NB, 128 / (bw * bh)) : 1;
+  while (NB % bn_img) --bn_img;
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int M = NB * Ho * Wo;
+  const int rc0 = fill_epilogue(p, epi, M, Cout);
+  if (rc0) return rc0;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t strides[3] = {(uint64_t)ldx, (uint64_t)ldx * W, (uint64_t)ldx * W * H};
+    uint32_t box[4] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn_img};
+    if (int rc = encode_tmap_f16(&p.tmA, x, 4, dims, strides, box, true)) return rc;
+    p.a_rank = 4;
+    for (int t = 0; t < 9; ++t) {
+      p.tap_off[t][0] = 0; p.tap_off[t][1] = t % 3 - 1; p.tap_off[t][2] = t / 3 - 1; p.tap_off[t][3] = 0; p.tap_off[t][4] = 0;
+    }
+  } else {
+    // stride 2: view the input as (c|px : 2*ldx, x' : W/2, y' : H/2, n, py : 2); tap (ky,kx) reads phase (py,px) shifted by {-1,0}
+    uint64_t dims[5] = {(uint64_t)(ldx + Cin), (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB, 2};
+    uint64_t strides[4] = {(uint64_t)2 * ldx, (uint64_t)2 * ldx * W, (uint64_t)ldx * W * H, (uint64_t)ldx * W};
+    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn_img, 1};
+    if (int rc = encode_tmap_f16(&p.tmA, x, 5, dims, strides, box, true)) return rc;
+    p.a_rank = 5;
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
+      p.tap_off[t][0] = px * (int)ldx;
+      p.tap_off[t][1] = (kx == 0) ? -1 : 0;
+      p.tap_off[t][2] = (ky == 0) ? -1 : 0;
+      p.tap_off[t][3] = 0;
+      p.tap_off[t][4] = py;
+    }
+  }
+  const int bn = pick_block_n(Cout, p.mode, force_block_n);
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
+    uint64_t strides[2] = {(uint64_t)Cin, (uint64_t)Cin * Cout};
+    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    if (int rc = encode_tmap_f16(&p.tmB, w, 3, dims, strides, box, true)) return rc;
+  }
+  p.M = M; p.rows_per_tile = bw * bh * bn_img; p.a_box_bytes = p.rows_per_tile * 128;
+  p.k_blocks = (Cin + kBlockK - 1) / kBlockK; p.num_taps = 9;
+  p.m_tiles = M / p.rows_per_tile;
+  p.ndecomp = 3; p.dimsz[0] = Wo; p.dimsz[1] = Ho; p.dimsz[2] = NB;
+  p.out = static_cast<__half*>(out); p.ldo = ldo;
+  return dispatch_tapgemm(p, Cout, bn, stream);
+}
+
+// Temporal Conv1d(k=3, padding 1, no bias) over the frame axis: x [B, F, HW, Cin] fp16 (row stride ldx), w [3][Cout][Cin].
+// out[b,f,p,:] = sum_t w[t] * x[b, f+t-1, p, :]  (+ epilogue: residual = identity skip of the LoRA, group_bias = time embedding).
+extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout, const fz_epilogue_t* epi,
+                             void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && w && out, "fz_tconv3: null pointer");
+  FZ_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "fz_tconv3: Cin/ldx must be multiples of 8");
+  int bp = std::min(HW, 128);
+  while (HW % bp) --bp;
+  int bf = (bp == HW) ? std::min(F, 128 / bp) : 1;
+  while (F % bf) --bf;
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int M = B * F * HW;
+  const int rc0 = fill_epilogue(p, epi, M, Cout);
+  if (rc0) return rc0;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)F, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)ldx, (uint64_t)ldx * HW, (uint64_t)ldx * HW * F};
+    uint32_t box[4] = {kBlockK, (uint32_t)bp, (uint32_t)bf, 1};
+    if (int rc = encode_tmap_f16(&p.tmA, x, 4, dims, strides, box, true)) return rc;
+  }
+  p.a_rank = 4;
+  for (int t = 0; t < 3; ++t) { p.tap_off[t][2] = t - 1; }
+  const int bn = pick_block_n(Cout, p.mode, force_block_n);
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 3};
+    uint64_t strides[2] = {(uint64_t)Cin, (uint64_t)Cin * Cout};
+    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    if (int rc = encode_tmap_f16(&p.tmB, w, 3, dims, strides, box, true)) return rc;
+  }
+  p.M = M; p.rows_per_tile = bp * bf; p.a_box_bytes = p.rows_per_tile * 128;
+  p.k_blocks = (Cin + kBlockK - 1) / kBlockK; p.num_taps = 3;
+  p.m_tiles = M / p.rows_per_tile;
+  p.ndecomp = 3; p.dimsz[0] = HW; p.dimsz[1] = F; p.dimsz[2] = B;
+  p.out = static_cast<__half*>(out); p.ldo = ldo;
+  return dispatch_tapgemm(p, Cout, bn, stream);
+}
