@@ -17,7 +17,7 @@ class Epilogue(C.Structure):
     """fz_epilogue_t"""
     _fields_ = [
         ("bias", c_void_p), ("group_bias", c_void_p), ("rows_per_group", c_int), ("residual", c_void_p), ("ldr", c_ll),
-        ("mode", c_int), ("vt_col_start", c_int), ("out_vt", c_void_p), ("vt_S", c_int), ("vt_d", c_int),
+        ("residual2", c_void_p), ("ldr2", c_ll), ("mode", c_int), ("vt_col_start", c_int), ("out_vt", c_void_p), ("vt_S", c_int), ("vt_d", c_int),
         ("vt_heads", c_int), ("vt_ld", c_int),
     ]
 

@@ -47,6 +47,8 @@ struct TapGemmParams {
   int rows_per_group;
   const __half* residual;    // [M, ldr] or null
   long long ldr;
+  const __half* residual2;   // second skip tensor [M, ldr2] or null
+  long long ldr2;
   __half* out;
   long long ldo;
   int mode;          // FZ_EPI_ROWMAJOR / FZ_EPI_GEGLU
@@ -254,7 +256,13 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                 if (col < p.N) {
                   __align__(16) __half hv[8];
                   __align__(16) __half rv[8];
+                  __align__(16) __half rv2[8];
                   const bool full8 = col + 8 <= p.N;
+                  if (p.residual2) {
+                    if (full8) *reinterpret_cast<uint4*>(rv2) = *reinterpret_cast<const uint4*>(p.residual2 + m * p.ldr2 + col);
+                    else
+                      for (int e = 0; e < 8; ++e) rv2[e] = (col + e < p.N) ? p.residual2[m * p.ldr2 + col + e] : __half(0.f);
+                  }
                   if (p.residual) {
                     if (full8) *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col);
                     else
@@ -267,6 +275,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                       if (p.bias) v += p.bias[col + e];
                       if (gb) v += gb[col + e];
                       if (p.residual) v += __half2float(rv[e]);
+                      if (p.residual2) v += __half2float(rv2[e]);
                     }
                     hv[e] = __float2half_rn(v);
                   }
@@ -354,12 +363,13 @@ static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cuda
 }
 
 static int fill_epilogue(TapGemmParams& p, const fz_epilogue_t* e, int M, int gemm_cols) {
-  p.bias = nullptr; p.group_bias = nullptr; p.rows_per_group = 1; p.residual = nullptr; p.ldr = 0;
+  p.bias = nullptr; p.group_bias = nullptr; p.rows_per_group = 1; p.residual = nullptr; p.ldr = 0; p.residual2 = nullptr; p.ldr2 = 0;
   p.mode = FZ_EPI_ROWMAJOR; p.vt_col_start = INT_MAX; p.out_vt = nullptr; p.vt_S = p.vt_d = p.vt_heads = p.vt_ld = 1;
   p.N = gemm_cols;
   if (!e) return FZ_OK;
   p.bias = e->bias; p.group_bias = e->group_bias; p.rows_per_group = e->rows_per_group > 0 ? e->rows_per_group : 1;
   p.residual = static_cast<const __half*>(e->residual); p.ldr = e->ldr;
+  p.residual2 = static_cast<const __half*>(e->residual2); p.ldr2 = e->ldr2;
   p.mode = e->mode;
   if (e->mode == FZ_EPI_GEGLU) {
     FZ_CHECK_ARG(gemm_cols % 2 == 0, "GEGLU needs an even number of GEMM columns");

@@ -51,7 +51,7 @@ def pack_geglu(weight: torch.Tensor, bias: Optional[torch.Tensor]):
     return w, b, bn
 
 
-def _epilogue(bias=None, group_bias=None, rows_per_group=0, residual=None, geglu=False, vt_out=None, vt_col_start=0, vt_S=0, vt_d=0,
+def _epilogue(bias=None, group_bias=None, rows_per_group=0, residual=None, geglu=False, residual2=None, vt_out=None, vt_col_start=0, vt_S=0, vt_d=0,
               vt_heads=0, vt_ld=0) -> Epilogue:
     e = Epilogue()
     e.bias = _p(bias)
@@ -59,6 +59,8 @@ def _epilogue(bias=None, group_bias=None, rows_per_group=0, residual=None, geglu
     e.rows_per_group = int(rows_per_group)
     e.residual = _p(residual)
     e.ldr = residual.stride(-2) if residual is not None else 0
+    e.residual2 = _p(residual2)
+    e.ldr2 = residual2.stride(-2) if residual2 is not None else 0
     e.mode = _lib.EPI_GEGLU if geglu else _lib.EPI_ROWMAJOR
     e.out_vt = _p(vt_out)
     e.vt_col_start = int(vt_col_start)
@@ -101,16 +103,19 @@ def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias=None, stride: int = 1, resid
     return out
 
 
-def tconv3(x: torch.Tensor, w3: torch.Tensor, bias=None, residual=None, group_bias=None, rows_per_group=0, force_bn: int = 0):
+def tconv3(x: torch.Tensor, w3: torch.Tensor, bias=None, residual=None, group_bias=None, rows_per_group=0, force_bn: int = 0,
+           residual2=None):
     """x [B,F,HW,Cin], w3 [3,Cout,Cin]: Conv1d(k=3,pad=1) over F -> [B,F,HW,Cout] (+bias +residual +group_bias)."""
     _chk(x, f16, "tconv3"); _chk(w3, f16, "tconv3")
     B, F, HW, Cin = x.shape
     Cout = w3.shape[1]
     assert x.is_contiguous() and w3.is_contiguous()
     out = torch.empty((B, F, HW, Cout), dtype=f16, device=x.device)
-    e = _epilogue(bias, group_bias, rows_per_group, residual)
+    e = _epilogue(bias, group_bias, rows_per_group, residual, residual2=residual2)
     if residual is not None:
         e.ldr = residual.shape[-1]
+    if residual2 is not None:
+        e.ldr2 = residual2.shape[-1]
     _lib.call("fz_tconv3_f16", _p(x), Cin, B, F, HW, Cin, _p(w3), Cout, C.byref(e), _p(out), Cout, force_bn, _stream())
     return out
 

@@ -37,6 +37,8 @@ typedef struct fz_epilogue {
   int rows_per_group;      /*   (resnet.py:355-366 `hidden_states + temb`)                                        */
   const void* residual;    /* [M, ldr] fp16 or NULL: `+ hidden_states` skip connections                           */
   long long ldr;
+  const void* residual2;   /* second skip tensor (resnet shortcut next to the LoRA identity skip) or NULL           */
+  long long ldr2;
   int mode;                /* FZ_EPI_GEGLU: columns [0,BN/2) x, [BN/2,BN) gate per tile -> x*gelu(gate)           */
   int vt_col_start;        /* columns >= vt_col_start are stored transposed into out_vt (V^T for the PV GEMM)     */
   void* out_vt;            /* [M / vt_S, vt_heads, vt_d, vt_S] fp16 or NULL                                       */
