@@ -1,0 +1,360 @@
+"""UNetEngine — executes one UNetPseudo3DConditionModel forward with the sm_100a kernels of libfatezero_b200.so.
+
+Data layout in HBM: every activation is fp16 channels-last, `[B*F, H, W, C]` == token-major `[B*F*H*W, C]` (frame-minor batch
+order like the reference's "(b f)" rearranges), so conv / linear / attention kernels read and write the same buffers without
+transposes; weights are packed once per model into fp16 K-major matrices (`[9][Cout][Cin]` for 3x3 convs, `[3][Cout][Cin]` for the
+temporal LoRA, `[N][K]` for linears, tile-interleaved for GEGLU, Q|K|V fused).  Text K / V^T of all 16 cross-attention layers are
+computed once per prompt (they are constant over frames and steps: models/attention.py:104).
+
+Reference forward restated: models/unet_3d_condition.py:307-446 (+ unet_3d_blocks.py, resnet.py:335-394, attention.py:95-144,271-337).
+The attention controller is not called back per layer; it is asked for kernel arguments (`self_attn_args` / `cross_attn_args`)
+and the STORE / INJECT / BLEND work happens inside fz_attention_f16.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+
+f16 = torch.float16
+f32 = torch.float32
+
+
+def sc_frame_indices(index_list, clip_length: int) -> List[List[int]]:
+    """Source frame of every query frame, per K/V slot (attention_register.py:168-188)."""
+    out = []
+    for index in index_list:
+        if isinstance(index, str):
+            if index == "first":
+                fi = [0] * clip_length
+            elif index == "last":
+                fi = [clip_length - 1] * clip_length
+            elif index in ("mid", "middle"):
+                fi = [int((clip_length - 1) // 2)] * clip_length
+            else:
+                raise ValueError(f"unknown SparseCausalAttention_index entry {index!r}")
+        else:
+            if not isinstance(index, int):
+                raise AssertionError("relative index must be int")
+            fi = [min(max(f + index, 0), clip_length - 1) for f in range(clip_length)]
+        out.append(fi)
+    return out
+
+
+class UNetEngine:
+    def __init__(self, unet, exact_skips: bool = True):
+        dev = unet.device
+        if dev.type != "cuda":
+            raise RuntimeError("UNetEngine needs the UNet parameters on a CUDA device (sm_100a); no CPU fallback exists")
+        lib = _lib.load()
+        _lib.check(lib.fz_device_check(), "fz_device_check")
+        self.cfg = dict(unet.config)
+        self.mc = dict(unet.model_config)
+        self.dev = dev
+        self.heads = self.cfg["attention_head_dim"]
+        self.groups = self.cfg["norm_num_groups"]
+        self.eps = float(self.cfg["norm_eps"])
+        self.ch = list(self.cfg["block_out_channels"])
+        self.exact_skips = exact_skips
+        self.w: Dict[str, torch.Tensor] = {}
+        self._text_key = None
+        self._text_kv: Dict[str, tuple] = {}
+        self._prepare({k: v.detach() for k, v in unet.state_dict().items()})
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # weight packing
+    # ---------------------------------------------------------------------------------------------------------------
+    def _prepare(self, sd: Dict[str, torch.Tensor]):
+        w = self.w
+        dev = self.dev
+
+        def h(t):
+            return t.to(dev, f16).contiguous()
+
+        def f(t):
+            return t.to(dev, f32).contiguous()
+
+        self.has = set(sd.keys())
+        self.lora_skip = {}
+        for name, t in sd.items():
+            if name.endswith(".weight") and t.dim() == 4 and t.shape[-1] == 3 and name not in ("conv_in.weight",):
+                co, ci = t.shape[:2]
+                if name == "conv_out.weight":
+                    w9 = torch.zeros(9, 16, ci)
+                    w9[:, :co] = t.permute(2, 3, 0, 1).reshape(9, co, ci)
+                    w[name] = h(w9)  # padded to one 16-wide MMA tile
+                else:
+                    w[name] = h(t.permute(2, 3, 0, 1).reshape(9, co, ci))
+            elif name == "conv_in.weight":
+                co, ci = t.shape[:2]
+                wp = torch.zeros(co, 64)
+                wp[:, : 9 * ci] = t.permute(0, 2, 3, 1).reshape(co, 9 * ci)  # col = tap*Cin + c
+                w[name] = h(wp)
+            elif name.endswith(".weight") and t.dim() == 4 and t.shape[-1] == 1:
+                w[name] = h(t.reshape(t.shape[0], t.shape[1]))
+            elif "conv_temporal" in name and name.endswith(".weight") and t.dim() == 3:
+                if name.startswith("conv_out."):
+                    w[name + "#f32"] = f(t)  # tiny (C=4): handled by fz_out_temporal_f32
+                w[name] = h(t.permute(2, 0, 1))  # [3][Cout][Cin]
+            elif name == "conv_out.bias":
+                w[name] = f(torch.nn.functional.pad(t.float(), (0, 16 - t.shape[0])))
+            elif name.endswith(".time_emb_proj.weight") or any(name.endswith(sfx) for sfx in (
+                    "attn1.to_q.weight", "attn1.to_k.weight", "attn1.to_v.weight", "attn2.to_k.weight", "attn2.to_v.weight",
+                    "attn_temporal.to_q.weight", "attn_temporal.to_k.weight", "attn_temporal.to_v.weight")):
+                continue  # only used through the fused matrices built below
+            elif name.endswith("ff.net.0.proj.weight"):
+                pw, pb, bn = ops.pack_geglu(t.float(), sd[name[:-6] + "bias"].float())
+                w[name] = h(pw)
+                w[name[:-6] + "bias"] = f(pb)
+                w[name + "#bn"] = bn
+            elif name.endswith("ff.net.0.proj.bias"):
+                continue
+            elif name.endswith(".weight") and t.dim() == 2:
+                w[name] = h(t)
+            else:
+                w[name] = f(t)
+        # fused projections
+        for name in list(sd.keys()):
+            if name.endswith("attn1.to_q.weight"):
+                p = name[: -len("to_q.weight")]
+                w[p + "qkv"] = h(torch.cat([sd[p + "to_q.weight"], sd[p + "to_k.weight"], sd[p + "to_v.weight"]], 0))
+            if name.endswith("attn_temporal.to_q.weight"):
+                p = name[: -len("to_q.weight")]
+                w[p + "qkv"] = h(torch.cat([sd[p + "to_q.weight"], sd[p + "to_k.weight"], sd[p + "to_v.weight"]], 0))
+            if name.endswith("attn2.to_k.weight"):
+                p = name[: -len("to_k.weight")]
+                w[p + "kv"] = h(torch.cat([sd[p + "to_k.weight"], sd[p + "to_v.weight"]], 0))
+        # exact algebraic skips (identity temporal layers of un-tuned SD weights: lora.py:42, models/attention.py:224)
+        for name, t in sd.items():
+            if name.endswith("conv_temporal.up.weight"):
+                self.lora_skip[name[: -len(".conv_temporal.up.weight")]] = self.exact_skips and bool((t == 0).all())
+            if name.endswith("attn_temporal.to_out.0.weight") and self.exact_skips and bool((t == 0).all()):
+                tp = name[: -len(".transformer_blocks.0.attn_temporal.to_out.0.weight")]
+                bt = sd[name[:-6] + "bias"].float()
+                wpo = sd[tp + ".proj_out.weight"].float().reshape(bt.shape[0], -1)
+                # proj_out(h + b_t) = proj_out(h) + W_po b_t : fold the constant into the proj_out bias
+                w[tp + ".proj_out.bias#folded"] = f(sd[tp + ".proj_out.bias"].float() + wpo @ bt)
+        # the 22 time_emb_proj layers as one row-vector GEMM
+        names = [n[: -len(".time_emb_proj.weight")] for n in sd if n.endswith(".time_emb_proj.weight")]
+        self.temb_slices = {}
+        off = 0
+        ws, bs = [], []
+        for n in names:
+            co = sd[n + ".time_emb_proj.weight"].shape[0]
+            self.temb_slices[n] = (off, off + co)
+            off += co
+            ws.append(sd[n + ".time_emb_proj.weight"])
+            bs.append(sd[n + ".time_emb_proj.bias"])
+        w["#temb_proj.weight"] = h(torch.cat(ws, 0))
+        w["#temb_proj.bias"] = f(torch.cat(bs, 0))
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # text K / V^T cache (attention_register.py:99-100 recomputes these per frame, layer and step)
+    # ---------------------------------------------------------------------------------------------------------------
+    def _ensure_text(self, text: torch.Tensor):
+        key = (text.data_ptr(), tuple(text.shape), text._version)
+        if key == self._text_key:
+            return
+        B, L, D = text.shape
+        if L != 77:
+            raise NotImplementedError("cross-attention expects 77 text tokens (CLIP max length)")
+        t16 = text.to(self.dev, f16).reshape(B * L, D).contiguous()
+        self._text_kv = {}
+        for name in self.w:
+            if name.endswith("attn2.kv"):
+                wkv = self.w[name]
+                c = wkv.shape[0] // 2
+                d = c // self.heads
+                vt = torch.zeros((B, self.heads, d, 80), dtype=f16, device=self.dev)
+                k = ops.gemm(t16, wkv, vt=dict(out=vt, col_start=c, S=L, d=d, heads=self.heads, ld=80))
+                self._text_kv[name[: -len(".kv")]] = (k, vt)
+        self._text_key = key
+        self._text_ref = text  # keep alive so data_ptr stays unique
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # building blocks
+    # ---------------------------------------------------------------------------------------------------------------
+    def _temporal(self, name: str, y: torch.Tensor, B: int, F: int, group_bias=None, residual2=None) -> torch.Tensor:
+        """y [B*F, H, W, C] conv output -> temporal conv (resnet.py:72-78) fused with +temb / +shortcut."""
+        w = self.w
+        NB, H, W, C = y.shape
+        M = NB * H * W
+        y4 = y.view(B, F, H * W, C)
+        if name + ".conv_temporal.down.weight" in w:
+            mid = ops.tconv3(y4, w[name + ".conv_temporal.down.weight"])
+            out = ops.tconv3(mid, w[name + ".conv_temporal.up.weight"], residual=y4, residual2=residual2, group_bias=group_bias,
+                             rows_per_group=M)
+        else:
+            out = ops.tconv3(y4, w[name + ".conv_temporal.weight"], bias=w[name + ".conv_temporal.bias"], residual2=residual2,
+                             group_bias=group_bias, rows_per_group=M)
+        return out.view(NB, H, W, C)
+
+    def _has_temporal(self, name: str) -> bool:
+        if name + ".conv_temporal.down.weight" in self.w:
+            return not self.lora_skip.get(name, False)
+        return name + ".conv_temporal.weight" in self.w
+
+    def conv(self, name: str, x: torch.Tensor, B: int, F: int, stride: int = 1, group_bias=None, residual=None) -> torch.Tensor:
+        """PseudoConv3d.forward for k=3 (resnet.py:57-80), with the epilogue additions of the caller fused in."""
+        w = self.w
+        M_out = x.shape[0] * (x.shape[1] // stride) * (x.shape[2] // stride)
+        if self._has_temporal(name):
+            y = ops.conv3x3(x, w[name + ".weight"], bias=w[name + ".bias"], stride=stride)
+            return self._temporal(name, y, B, F, group_bias=group_bias, residual2=residual)
+        return ops.conv3x3(x, w[name + ".weight"], bias=w[name + ".bias"], stride=stride, residual=residual, group_bias=group_bias,
+                           rows_per_group=M_out)
+
+    def resnet(self, p: str, x: torch.Tensor, temb_all: torch.Tensor, B: int, F: int) -> torch.Tensor:
+        """ResnetBlockPseudo3D.forward (resnet.py:335-394)."""
+        w = self.w
+        NB, H, W, Cin = x.shape
+        n1 = ops.groupnorm(x.view(NB, H * W, Cin), w[p + ".norm1.weight"], w[p + ".norm1.bias"], self.eps, self.groups, F, True)
+        a, b = self.temb_slices[p]
+        tb = temb_all[a:b].view(1, b - a)
+        h = self.conv(p + ".conv1", n1.view(NB, H, W, Cin), B, F, group_bias=tb)
+        Cout = h.shape[-1]
+        n2 = ops.groupnorm(h.view(NB, H * W, Cout), w[p + ".norm2.weight"], w[p + ".norm2.bias"], self.eps, self.groups, F, True)
+        if p + ".conv_shortcut.weight" in w:
+            sc = ops.gemm(x.view(-1, Cin), w[p + ".conv_shortcut.weight"], bias=w[p + ".conv_shortcut.bias"]).view(NB, H, W, Cout)
+        else:
+            sc = x
+        return self.conv(p + ".conv2", n2.view(NB, H, W, Cout), B, F, residual=sc)
+
+    def transformer(self, p: str, x: torch.Tensor, B: int, F: int, place: str, ctrl) -> torch.Tensor:
+        """SpatioTemporalTransformerModel.forward + Block.forward (models/attention.py:95-144,271-337)."""
+        w = self.w
+        NB, H, W, C = x.shape
+        S = H * W
+        M = NB * S
+        heads = self.heads
+        d = C // heads
+        scale = d ** -0.5
+        bp = p + ".transformer_blocks.0"
+        xr = x.view(M, C)
+        n = ops.groupnorm(x.view(NB, S, C), w[p + ".norm.weight"], w[p + ".norm.bias"], 1e-6, self.groups, 1, False)
+        h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"])
+        # ---- attn1: sparse-causal spatio-temporal self-attention (attention_register.py:131-218)
+        if "SparseCausalAttention_index" in self.mc:
+            index_list = list(self.mc["SparseCausalAttention_index"])
+        else:
+            index_list = [-1, "first"]
+        if "least_sc_channel" in self.mc and C < self.mc["least_sc_channel"]:
+            index_list = []
+        fis = sc_frame_indices(index_list, F) if index_list else [list(range(F))]
+        src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]
+        ln1 = ops.layernorm(h, w[bp + ".norm1.weight"], w[bp + ".norm1.bias"])
+        vt = torch.empty((NB, heads, d, S), dtype=f16, device=self.dev)
+        qk = ops.gemm(ln1, w[bp + ".attn1.qkv"], vt=dict(out=vt, col_start=2 * C, S=S, d=d, heads=heads))
+        o = torch.empty((M, C), dtype=f16, device=self.dev)
+        kw = {}
+        if ctrl is not None and S <= 32 ** 2:
+            kw = ctrl.self_attn_args(place, S, len(src_index) * S, heads, NB, F) or {}
+        ops.attention(qk[:, :C], qk[:, C:], vt, o, S_q=S, keys_per_slot=S, n_src=NB, d=d, heads=heads, F=F, BF=NB, scale=scale,
+                      src_index=src_index, **kw)
+        h = ops.gemm(o, w[bp + ".attn1.to_out.0.weight"], bias=w[bp + ".attn1.to_out.0.bias"], residual=h)
+        # ---- attn2: text cross-attention (attention_register.py:71-128)
+        ln2 = ops.layernorm(h, w[bp + ".norm2.weight"], w[bp + ".norm2.bias"])
+        q2 = ops.gemm(ln2, w[bp + ".attn2.to_q.weight"])
+        kt, vtt = self._text_kv[bp + ".attn2"]
+        kw = {}
+        if ctrl is not None and S <= 32 ** 2:
+            kw = ctrl.cross_attn_args(place, S, heads, NB, F) or {}
+        o2 = torch.empty((M, C), dtype=f16, device=self.dev)
+        ops.attention(q2, kt, vtt, o2, S_q=S, keys_per_slot=77, n_src=B, d=d, heads=heads, F=F, BF=NB, scale=scale,
+                      src_index=[[b for b in range(B) for _ in range(F)]], **kw)
+        h = ops.gemm(o2, w[bp + ".attn2.to_out.0.weight"], bias=w[bp + ".attn2.to_out.0.bias"], residual=h)
+        # ---- feed-forward (GEGLU)
+        ln3 = ops.layernorm(h, w[bp + ".norm3.weight"], w[bp + ".norm3.bias"])
+        g = ops.gemm(ln3, w[bp + ".ff.net.0.proj.weight"], bias=w[bp + ".ff.net.0.proj.bias"], geglu=True,
+                     force_bn=w[bp + ".ff.net.0.proj.weight#bn"])
+        h = ops.gemm(g, w[bp + ".ff.net.2.weight"], bias=w[bp + ".ff.net.2.bias"], residual=h)
+        # ---- temporal attention over frames (models/attention.py:327-337), un-hooked
+        po_bias = w[p + ".proj_out.bias"]
+        if p + ".proj_out.bias#folded" in w:
+            po_bias = w[p + ".proj_out.bias#folded"]  # to_out.weight == 0: the layer adds its bias only
+        else:
+            lnt = ops.layernorm(h, w[bp + ".norm_temporal.weight"], w[bp + ".norm_temporal.bias"])
+            qkvt = ops.gemm(lnt, w[bp + ".attn_temporal.qkv"])
+            ot = ops.temporal_attn(qkvt, B, F, S, heads, d, scale)
+            h = ops.gemm(ot, w[bp + ".attn_temporal.to_out.0.weight"], bias=w[bp + ".attn_temporal.to_out.0.bias"], residual=h)
+        out = ops.gemm(h, w[p + ".proj_out.weight"], bias=po_bias, residual=xr)
+        return out.view(NB, H, W, C)
+
+    def time_embedding(self, t: float) -> torch.Tensor:
+        """time_proj + time_embedding + all time_emb_proj(SiLU(emb)) rows (unet_3d_condition.py:356-362; resnet.py:355)."""
+        w = self.w
+        c0 = self.ch[0]
+        s = ops.timestep_sinusoid(t, c0, bool(self.cfg.get("flip_sin_to_cos", True)), float(self.cfg.get("freq_shift", 0)), self.dev)
+        e = ops.rowvec_linear(s, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], False)
+        emb = ops.rowvec_linear(e, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"], True)
+        return ops.rowvec_linear(emb, w["#temb_proj.weight"], w["#temb_proj.bias"], True)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: float, text: torch.Tensor, ctrl=None) -> torch.Tensor:
+        """x [B,4,F,H,W] (any float dtype, CUDA), text [B,77,D] -> eps [B,4,F,H,W] fp32."""
+        if ctrl is not None and not hasattr(ctrl, "self_attn_args"):
+            if type(ctrl).__name__ in ("EmptyControl", "DummyController"):
+                ctrl = None
+            else:
+                raise NotImplementedError(
+                    f"controller {type(ctrl).__name__} does not implement the fused-kernel protocol (self_attn_args / cross_attn_args); "
+                    "use the controllers of video_diffusion.prompt_attention.attention_util")
+        w = self.w
+        B, Cl, F, H, W = x.shape
+        NB = B * F
+        if text.shape[0] != B:
+            raise ValueError(f"encoder_hidden_states batch {text.shape[0]} != sample batch {B}")
+        self._ensure_text(text)
+        if ctrl is not None:
+            ctrl.begin_forward(B, F)
+        temb_all = self.time_embedding(t)
+        xf = x.to(f32).contiguous()
+        cols = ops.im2col_latents(xf)
+        c0 = self.ch[0]
+        h = ops.gemm(cols, w["conv_in.weight"], bias=w["conv_in.bias"]).view(NB, H, W, c0)
+        if self._has_temporal("conv_in"):
+            h = self._temporal("conv_in", h, B, F)
+        skips = [h]
+        nblk = len(self.ch)
+        lpb = self.cfg["layers_per_block"]
+        for i, btype in enumerate(self.cfg["down_block_types"]):
+            p = f"down_blocks.{i}"
+            for j in range(lpb):
+                h = self.resnet(f"{p}.resnets.{j}", h, temb_all, B, F)
+                if btype.startswith("CrossAttn"):
+                    h = self.transformer(f"{p}.attentions.{j}", h, B, F, "down", ctrl)
+                skips.append(h)
+            if i != nblk - 1:
+                h = self.conv(f"{p}.downsamplers.0.conv", h, B, F, stride=2)
+                skips.append(h)
+        h = self.resnet("mid_block.resnets.0", h, temb_all, B, F)
+        h = self.transformer("mid_block.attentions.0", h, B, F, "mid", ctrl)
+        h = self.resnet("mid_block.resnets.1", h, temb_all, B, F)
+        for i, btype in enumerate(self.cfg["up_block_types"]):
+            p = f"up_blocks.{i}"
+            for j in range(lpb + 1):
+                h = ops.concat_channels(h, skips.pop())
+                h = self.resnet(f"{p}.resnets.{j}", h, temb_all, B, F)
+                if btype.startswith("CrossAttn"):
+                    h = self.transformer(f"{p}.attentions.{j}", h, B, F, "up", ctrl)
+            if i != nblk - 1:
+                h = self.conv(f"{p}.upsamplers.0.conv", ops.upsample2x(h), B, F)
+        NBh, Hh, Wh, Ch = h.shape
+        n = ops.groupnorm(h.view(NB, Hh * Wh, Ch), w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.eps, self.groups, F, True)
+        co = self.cfg["out_channels"]
+        # conv_out as one 16-wide MMA tile (first `co` channels valid); its bias precedes the temporal conv (resnet.py:64 then :76)
+        y = ops.conv3x3(n.view(NB, Hh, Wh, Ch), w["conv_out.weight"], bias=w["conv_out.bias"])
+        return self._finish(y.view(NB * Hh * Wh, 16), B, co, F, Hh, Wh)
+
+    def _finish(self, y, B, co, F, H, W):
+        w = self.w
+        kw = {}
+        if "conv_out.conv_temporal.down.weight" in w:
+            if not self.lora_skip.get("conv_out", False):
+                kw = dict(down=w["conv_out.conv_temporal.down.weight#f32"], up=w["conv_out.conv_temporal.up.weight#f32"])
+        elif "conv_out.conv_temporal.weight" in w:
+            kw = dict(w_full=w["conv_out.conv_temporal.weight#f32"], b_full=w["conv_out.conv_temporal.bias"])
+        return ops.out_temporal(y, B, co, F, H, W, **kw)

@@ -1,0 +1,24 @@
+"""Parity cases shared by oracle/make_golden.py (reference run, build container) and the tests (oracle / CUDA runs).
+Each case fixes geometry, model_config, prompts, steps and the p2p_config of one edit; inputs come from fatezero_b200.synth."""
+SRC = "a silver jeep driving down a curvy road in the countryside"
+
+CASES = {
+    # config #1-like: Refine + Reweight (config/low_resource_teaser/jeep_watercolor_ddim_10_steps.yaml), small geometry
+    "mini_refine": dict(
+        unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128),
+        frames=3, size=32, steps=4, source=SRC, target="watercolor painting of " + SRC,
+        p2p=dict(is_replace_controller=False, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.8,
+                 eq_params={"words": ["watercolor"], "values": [10, 10]})),
+    # config #3-like: Replace + self-attention mask blend + latent blend (config/teaser/jeep_posche_local_latent_blend.yaml)
+    "mini_replace_blend": dict(
+        unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128),
+        frames=2, size=64, steps=5, source=SRC, target="a Porsche car driving down a curvy road in the countryside",
+        p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.5}, self_replace_steps=0.6,
+                 blend_words=[["silver", "jeep"], ["Porsche", "car"]], blend_self_attention=True, blend_latents=True,
+                 blend_th=[0.985, 0.985])),
+    # config #5-like semantics: default [-1, 'first'] K/V (two slots) at every level, no least_sc_channel
+    "mini_shape": dict(
+        unet="mini", model_config=dict(lora=160),
+        frames=3, size=32, steps=3, source="a silver jeep driving down a curvy road", target="a red jeep driving down a curvy road",
+        p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.7, "red": 0.4}, self_replace_steps=0.7)),
+}

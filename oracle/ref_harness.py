@@ -30,6 +30,11 @@ def _prepare_imports():
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
+    # a regular package (the repo's alias) beats the reference's namespace package in the path search: pin the name explicitly
+    import types
+    pkg = types.ModuleType("video_diffusion")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "video_diffusion")]
+    sys.modules["video_diffusion"] = pkg
     # models/attention.py:229 calls torch.cuda.get_device_name(0) for every block
     if not torch.cuda.is_available():
         torch.cuda.get_device_name = lambda *a, **k: "cpu-shim"

@@ -1,0 +1,113 @@
+"""Pipeline-level parity on the GPU: the CUDA product (through the reference-facing API) against
+  (a) oracle/fz_oracle.py run on the same seeded inputs, and
+  (b) the committed golden vectors produced by the unmodified reference (tests/golden/*.pt, oracle/make_golden.py).
+Tolerances: the product computes in fp16 storage / fp32 accumulation, the oracle and the reference fixtures are fp32 CPU runs,
+so the bounds below are fp16-propagation bounds (stated per test), not bit-exactness."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _helpers import GOLDEN_DIR, build_oracle, build_product, case_inputs, run_oracle_case, run_product_case  # noqa: E402
+from fatezero_b200 import synth  # noqa: E402
+from oracle.cases import CASES  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+@pytest.mark.parametrize("unet_name,mc,frames,size", [
+    ("mini", dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128), 3, 32),
+    ("mini", dict(lora=160), 2, 32),
+    ("mini", dict(SparseCausalAttention_index=["mid"]), 2, 32),
+    ("mid", dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=320), 2, 32),
+])
+def test_unet_forward_vs_oracle(unet_name, mc, frames, size, report):
+    """One CFG-batch UNet forward (no controller). Bound: max|d eps| <= 2% of max|eps| (fp16 activations through ~60 layers)."""
+    cfg = synth.UNET_CONFIGS[unet_name]
+    pipe = build_product(unet_name, mc)
+    ou = build_oracle(unet_name, mc)
+    x0 = synth.synth_latents(frames, size, size) * 0.5
+    x2 = torch.cat([x0, 0.7 * x0])
+    emb = torch.randn(2, 77, cfg["cross_attention_dim"], generator=torch.Generator().manual_seed(2))
+    ref = ou.forward(x2, 481, emb)
+    got = pipe.unet(x2.cuda(), 481, emb.cuda()).sample
+    r, a = rel(got, ref)
+    report[f"fwd_{unet_name}_{frames}_{size}_{len(mc)}"] = dict(rel=r, max_abs=a, ref_std=ref.std().item())
+    assert r < 2e-2, f"relative error {r:.3g} (abs {a:.3g})"
+
+
+def test_unet_forward_degenerate_temporal(report):
+    """SD-style weights (lora.up == 0, attn_temporal.to_out.weight == 0) exercise the exact-skip paths of the engine."""
+    mc = dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128)
+    pipe = build_product("mini", mc, degenerate_temporal=True)
+    ou = build_oracle("mini", mc, degenerate_temporal=True)
+    x0 = synth.synth_latents(2, 32, 32) * 0.5
+    emb = torch.randn(1, 77, 128, generator=torch.Generator().manual_seed(2))
+    ref = ou.forward(x0, 101, emb)
+    got = pipe.unet(x0.cuda(), 101, emb.cuda()).sample
+    r, a = rel(got, ref)
+    report["fwd_degenerate"] = dict(rel=r, max_abs=a)
+    assert r < 2e-2
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_case_vs_oracle_and_golden(name, report):
+    """Full inversion + edit of a parity case. Bounds (fp16 vs fp32 through 2N UNet forwards of an expansive random-init
+    sampler): inversion latents 2e-2 relative, final edit latents 8e-2 relative; stored maps 3e-3 absolute."""
+    case = CASES[name]
+    prod = run_product_case(case)
+    orc = run_oracle_case(case)
+    r_inv, a_inv = rel(prod["inv_latents"], orc["inv_latents"])
+    r_ed, a_ed = rel(prod["edit_latents"][-1], orc["edit_latents"][-1])
+    per_step = [rel(prod["edit_latents"][i], orc["edit_latents"][i])[0] for i in range(case["steps"])]
+    report[f"{name}_vs_oracle"] = dict(inv_rel=r_inv, inv_abs=a_inv, edit_rel=r_ed, edit_abs=a_ed, edit_rel_per_step=per_step)
+    # stored inversion maps of step 0 against the oracle's
+    store = prod["pipe"].store_controller
+    worst = 0.0
+    for key, lst in store.attention_store_all_step[0].items():
+        for pos, t in enumerate(lst):
+            o = orc["store"].all_step[0][key][pos]
+            worst = max(worst, (t.float().cpu() - o).abs().max().item())
+    report[f"{name}_maps"] = dict(max_abs=worst)
+    assert worst < 3e-3
+    assert r_inv < 2e-2 and r_ed < 8e-2, (r_inv, r_ed, per_step)
+    gpath = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    if os.path.exists(gpath):
+        g = torch.load(gpath)
+        rg_inv, _ = rel(prod["inv_latents"], g["inv_latents"])
+        rg_ed, ag_ed = rel(prod["edit_latents"][-1], g["edit_latents"][-1])
+        report[f"{name}_vs_golden"] = dict(inv_rel=rg_inv, edit_rel=rg_ed, edit_abs=ag_ed)
+        assert rg_inv < 2e-2 and rg_ed < 8e-2
+        if "mask_list" in g and prod["result"]["mask_list"]:
+            mism = max((a.cpu().reshape(-1) != b.reshape(-1)).float().mean().item() for a, b in zip(prod["result"]["mask_list"], g["mask_list"]))
+            report[f"{name}_mask_mismatch"] = mism
+            assert mism < 2e-2
+
+
+def test_sd14_single_forward(report):
+    """Full SD-1.4 geometry (head dims 40/80/160), one inversion-style forward with STORE on, 2 frames at 64x64 latents."""
+    from fatezero_b200 import controllers
+    mc = dict(synth.DEFAULT_MODEL_CONFIG)
+    pipe = build_product("sd14", mc)
+    ou = build_oracle("sd14", mc)
+    x0 = synth.synth_latents(2, 64, 64) * 0.5
+    emb = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(2))
+    from oracle import fz_oracle as fo
+    ostore = fo.OracleStore()
+    ref = ou.forward(x0, 481, emb, ostore.hook)
+    store = controllers.AttentionStore()
+    store.LOW_RESOURCE = True
+    controllers.register_attention_control(pipe, store)
+    got = pipe.unet(x0.cuda(), 481, emb.cuda()).sample
+    r, a = rel(got, ref)
+    worst = 0.0
+    for key, lst in store.step_store.items():
+        for pos, t in enumerate(lst):
+            worst = max(worst, (t.float().cpu() - ostore.step_store[key][pos]).abs().max().item())
+    report["sd14_forward"] = dict(rel=r, max_abs=a, maps_max_abs=worst, n_maps=sum(len(v) for v in store.step_store.values()))
+    assert r < 2e-2 and worst < 3e-3
