@@ -1,0 +1,332 @@
+"""bench.py — headline benchmark of the FateZero hot path on B200.
+
+metric  : edited frames/sec = F / (T_inversion + T_edit) for one 512x512x8-frame clip, 50 DDIM steps, one target prompt
+          (BASELINE.json / SURVEY.md §8(d)); one "step" of this script = ONE full clip edit (50 inversion UNet forwards with the
+          attention-map STORE + 50 CFG edit forwards with INJECT), random-init SD-1.4-geometry UNet, synthetic latents.
+value   : inputs already resident in HBM when the timed region starts.
+e2e     : the same edit through the reference-facing API with HOST buffers: per step the clean latents are copied from pinned host
+          memory and the edited latents are read back to the host inside the timed region.
+roofline: the dominant kernel is the tcgen05 tap-GEMM (convs + linears + temporal LoRA, 86% of the FLOPs): algorithmic FLOPs of all its
+          launches in one clip edit / the sum of their CUDA-event durations (instrumented extra pass), against the measured bf16 peak.
+Launch:  python bench.py [--gpus N --steps K --warmup W]   (N>1 under torch.distributed.run, one rank per GPU: independent clips per
+         rank, "weak" scaling, no data-path collective yet — see DESIGN.md §multi-GPU)
+         python bench.py --impl reference ...               (CPU arm: the oracle port of the reference on the host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAMES, SIZE, DDIM_STEPS = 8, 64, 50
+SRC = "a silver jeep driving down a curvy road in the countryside"
+TGT = "watercolor painting of a silver jeep driving down a curvy road in the countryside"
+P2P = dict(is_replace_controller=False, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.8,
+           eq_params={"words": ["watercolor"], "values": [10, 10]})  # config/style/jeep_watercolor.yaml p2p_config[1]
+MODEL_CONFIG = dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=640)
+WORKLOAD = "style edit (config/style): 512x512x8f, 50 DDIM steps, Refine+Reweight, SD-1.4 UNet geometry, synthetic weights/latents"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def build_pipe(device):
+    from fatezero_b200 import DDIMScheduler, P2pDDIMSpatioTemporalPipeline, UNetPseudo3DConditionModel, synth
+    from fatezero_b200.unet import unet_param_spec
+    cfg = synth.SD14_UNET_CONFIG
+    unet = UNetPseudo3DConditionModel(**cfg, **MODEL_CONFIG)
+    spec = unet_param_spec(dict(cfg), MODEL_CONFIG)
+    # non-degenerate temporal weights: nothing on the path is an identity that could be skipped
+    unet.load_state_dict(synth.synth_state_dict({k: v[0] for k, v in spec.items()}, seed=0, degenerate_temporal=False))
+    unet.to(device)
+    te = synth.ToyTextEncoder(cfg["cross_attention_dim"]).to(device)
+    pipe = P2pDDIMSpatioTemporalPipeline(synth.VaeStub(), te, synth.ToyTokenizer(), unet, DDIMScheduler())
+    pipe.scheduler.set_timesteps(DDIM_STEPS)
+    pipe.prepare_before_train_loop()
+    return pipe
+
+
+def edit_clip(pipe, x0_dev, emb_src):
+    """One full clip edit through the reference-facing API: inversion with STORE, then edit_type='swap'. Returns final latents."""
+    from fatezero_b200 import controllers
+    pipe.scheduler.set_timesteps(DDIM_STEPS)
+    pipe.store_controller = controllers.AttentionStore()
+    controllers.register_attention_control(pipe, pipe.store_controller)
+    pipe.store_controller.LOW_RESOURCE = True
+    inv = pipe.ddim_clean2noisy_loop(x0_dev, emb_src, pipe.store_controller)
+    pipe.store_controller.LOW_RESOURCE = False
+    out = pipe(prompt=TGT, source_prompt=SRC, edit_type="swap", image=None, strength=None, generator=None,
+               num_inference_steps=DDIM_STEPS, clip_length=FRAMES, guidance_scale=7.5, num_images_per_prompt=1, latents=inv[-1],
+               uncond_embeddings_list=None, save_path=None, height=8 * SIZE, width=8 * SIZE, output_type="latent",
+               use_inversion_attention=True, save_self_attention=False, **P2P)
+    return out["sdimage_output"].images
+
+
+def instrument_tapgemm(pipe, x0_dev, emb_src):
+    """Extra (untimed) clip edit with CUDA events around every tap-GEMM launch: (algorithmic FLOPs, seconds, launches)."""
+    from fatezero_b200 import ops
+    rec = []
+    stream = torch.cuda.current_stream()
+
+    def wrap(fn, flops_of):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            out = fn(*a, **k)
+            e.record(stream)
+            rec.append((flops_of(a, k, out), s, e))
+            return out
+        return inner
+
+    def gemm_flops(a, k, out):
+        M, K = a[0].shape
+        return 2.0 * M * a[1].shape[0] * K
+
+    def conv_flops(a, k, out):
+        return 2.0 * out.numel() / out.shape[-1] * a[1].shape[1] * a[1].shape[2] * 9 if a[1].shape[1] != 16 else \
+            2.0 * out.numel() / out.shape[-1] * 4 * a[1].shape[2] * 9  # conv_out: 4 real output channels in a 16-wide tile
+
+    def tconv_flops(a, k, out):
+        return 2.0 * out.numel() / out.shape[-1] * a[1].shape[1] * a[1].shape[2] * 3
+
+    saved = (ops.gemm, ops.conv3x3, ops.tconv3)
+    ops.gemm, ops.conv3x3, ops.tconv3 = wrap(ops.gemm, gemm_flops), wrap(ops.conv3x3, conv_flops), wrap(ops.tconv3, tconv_flops)
+    try:
+        edit_clip(pipe, x0_dev, emb_src)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm, ops.conv3x3, ops.tconv3 = saved
+    flops = sum(r[0] for r in rec)
+    secs = sum(r[1].elapsed_time(r[2]) for r in rec) / 1e3
+    return flops, secs, len(rec)
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from fatezero_b200 import _lib, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pipe = build_pipe(device)
+    x0_host = (synth.synth_latents(FRAMES, SIZE, SIZE, seed=1 + rank) * 0.5).pin_memory()
+    out_host = torch.empty_like(x0_host).pin_memory()
+    x0_dev = x0_host.to(device)
+    emb_src = pipe._encode_prompt(SRC, device, 1, True, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        edit_clip(pipe, x0_dev, emb_src)
+
+    def step_e2e():
+        xd = x0_host.to(device, non_blocking=True)
+        lat = edit_clip(pipe, xd, emb_src)
+        out_host.copy_(lat.float(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.kernel_launches
+    ms = timed(step_resident, args.steps)
+    launches = _lib.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    frames_total = FRAMES * world * args.steps
+    value = frames_total / (ms / 1e3)
+    e2e_value = frames_total / (ms_e2e / 1e3)
+    pk, pk_kind = peaks()
+    roof = cpu = None
+    if rank == 0:
+        flops, secs, n_launch = instrument_tapgemm(pipe, x0_dev, emb_src)
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
+        ach = flops / secs / 1e12
+        roof = dict(kernel="tapgemm_kernel (conv3x3 / linear / temporal-LoRA, tcgen05)", bound="tensor", achieved=round(ach, 1), peak=peak,
+                    unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None, peak_source=f"{pk_kind} sustained bf16 (MEASURED_PEAKS.json)",
+                    launches_per_clip=n_launch, algorithmic_tflop_per_clip=round(flops / 1e12, 1),
+                    kernel_seconds_per_clip=round(secs, 4), share_of_step=round(secs / (ms / 1e3 / args.steps), 3))
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample()
+    if rank == 0:
+        line = dict(metric="edited frames/sec (512x512x8f, 50 DDIM steps: inversion + attention-fused edit)", value=round(value, 4),
+                    unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 2),
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 (fp32 accumulate)", data="synthetic",
+                    config=dict(workload=WORKLOAD, frames=FRAMES, latent=f"{SIZE}x{SIZE}", ddim_steps=DDIM_STEPS,
+                                model_config=MODEL_CONFIG, parallelism=("single GPU" if world == 1 else f"{world} independent clips (replicas)"),
+                                l2="working set (36 GiB map cache + activations) far exceeds the 126 MB L2; no explicit flush"),
+                    clocks=clocks, e2e=dict(value=round(e2e_value, 4), unit="frames/s", h2d_bytes_per_step=x0_host.numel() * 4,
+                                            d2h_bytes_per_step=out_host.numel() * 4),
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (the oracle port of the reference on the host cores)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_seconds(frames: int = 1):
+    """One inversion step (STORE) + one CFG edit step (INJECT) of the same workload on `frames` frames, fp32, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fatezero_b200 import synth
+    from fatezero_b200.unet import unet_param_spec
+    from oracle import fz_oracle as fo
+    cfg = synth.SD14_UNET_CONFIG
+    spec = unet_param_spec(dict(cfg), MODEL_CONFIG)
+    ou = fo.OracleUNet(synth.synth_state_dict({k: v[0] for k, v in spec.items()}), cfg, MODEL_CONFIG)
+    tok, te = synth.ToyTokenizer(), synth.ToyTextEncoder(cfg["cross_attention_dim"])
+    emb_src, emb_tgt = fo.encode_prompts(tok, te, SRC), fo.encode_prompts(tok, te, TGT)
+    x0 = synth.synth_latents(frames, SIZE, SIZE) * 0.5
+    t0 = time.perf_counter()
+    store = fo.OracleStore()
+    inv = fo.invert(ou, x0, emb_src[1:], 1, store)
+    t1 = time.perf_counter()
+    plan = fo.EditPlan(tok, SRC, TGT, 1, P2P["cross_replace_steps"], 1.0, False, P2P["eq_params"])
+    ctrl = fo.OracleEdit(plan, store)
+    fo.edit(ou, inv[-1], emb_tgt, 1, ctrl)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline_sample():
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_inv, t_edit = cpu_sample_seconds(1)
+    per_frame_pair = t_inv + t_edit  # seconds for one (inversion step + edit step) of ONE frame
+    value = 1.0 / (DDIM_STEPS * per_frame_pair)  # frames / s: F frames take F * 50 * pair seconds
+    return dict(value=round(value, 6), unit="frames/s", cores=cores, kind="port",
+                sample=f"1 of 50 DDIM step pairs (inversion STORE step + CFG edit INJECT step) on 1 of 8 frames, fp32, {cores} threads; "
+                       f"measured {t_inv:.1f}s + {t_edit:.1f}s, scaled linearly in frames and steps")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        t_inv, t_edit = cpu_sample_seconds(1)
+        if i >= args.warmup:
+            times.append(t_inv + t_edit)
+        if time.perf_counter() - t_start > 240 and times:  # keep the whole arm within a few minutes
+            break
+    pair = sum(times) / len(times)
+    value = 1.0 / (DDIM_STEPS * pair)
+    sample = (f"each step = 1 of 50 DDIM step pairs on 1 of 8 frames (oracle port of the reference, fp32, {cores} threads), "
+              f"{len(times)} timed; scaled linearly in frames and steps")
+    line = dict(impl="reference", metric="edited frames/sec (512x512x8f, 50 DDIM steps: inversion + attention-fused edit)",
+                value=round(value, 6), unit="frames/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=len(times), warmup=args.warmup,
+                ms_per_step=round(pair * 1e3 * DDIM_STEPS * FRAMES, 1), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=WORKLOAD, frames=FRAMES, latent=f"{SIZE}x{SIZE}", ddim_steps=DDIM_STEPS,
+                                             model_config=MODEL_CONFIG),
+                cpu_baseline=dict(value=round(value, 6), unit="frames/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=round(value, 6), unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,7 +66,9 @@ SIGNATURES = {
 }
 
 _lib = None
-launch_count = 0  # number of C-ABI compute calls issued (bench.py reports kernels launched by this library)
+launch_count = 0     # C-ABI compute calls issued
+kernel_launches = 0  # kernels of this library launched (bench.py reports the delta over its timed region)
+KERNELS_PER_CALL = {"fz_groupnorm_nhwc_f16": 2}  # stats + apply (plus one memset); every other entry point launches one kernel
 
 
 def load():
@@ -95,7 +97,8 @@ def check(rc: int, what: str):
 
 
 def call(name: str, *args):
-    global launch_count
+    global launch_count, kernel_launches
     lib = load()
     launch_count += 1
+    kernel_launches += KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib, name)(*args), name)

@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
     int g = 0;
     if (!replace) {
       // ------------------------------ pass 1: row max (and sum when exact) ------------------------------
+      // m_run tracks the max of the RAW scores (scale > 0); exponent arguments are formed with one FFMA: s*scale_log2 - m*scale_log2
+      const float sc2 = p.scale_log2;
       for (int b = 0; b < n_blocks; ++b, ++g) {
         const int buf = g & 1;
         mbar_wait(&s_full[buf], (g >> 1) & 1);
@@ -280,30 +282,41 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
         const int na = min(2, n_atoms - 2 * b);
         for (int a = 0; a < na; ++a) {
           const int valid = atom_info(p, atoms_per_slot, 2 * b + a).valid;
-#pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + c, r);
-            tmem_ld_wait();
-            float cm = -INFINITY;
+          uint32_t r[64];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+          tmem_ld_wait();
+          if (valid < 64) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float s = (c + e < valid) ? __uint_as_float(r[e]) * p.scale_log2 : -INFINITY;
-              r[e] = __float_as_uint(s);
-              cm = fmaxf(cm, s);
-            }
-            if (exact) {
-              const float m_new = fmaxf(m_run, cm);
-              if (m_new > -INFINITY) {
-                float acc = 0.f;
+            for (int e = 0; e < 64; ++e)
+              if (e >= valid) r[e] = 0xff800000u;  // -inf
+          }
+          float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) acc += ex2(__uint_as_float(r[e]) - m_new);
-                l_run = l_run * ex2(m_run - m_new) + acc;
+          for (int e = 0; e < 64; e += 4) {
+            c0 = fmaxf(c0, __uint_as_float(r[e + 0]));
+            c1 = fmaxf(c1, __uint_as_float(r[e + 1]));
+            c2 = fmaxf(c2, __uint_as_float(r[e + 2]));
+            c3 = fmaxf(c3, __uint_as_float(r[e + 3]));
+          }
+          const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+          if (exact) {
+            const float m_new = fmaxf(m_run, cm);
+            if (m_new > -INFINITY) {
+              const float mb = m_new * sc2;
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+              for (int e = 0; e < 64; e += 4) {
+                a0 += ex2(fmaf(__uint_as_float(r[e + 0]), sc2, -mb));
+                a1 += ex2(fmaf(__uint_as_float(r[e + 1]), sc2, -mb));
+                a2 += ex2(fmaf(__uint_as_float(r[e + 2]), sc2, -mb));
+                a3 += ex2(fmaf(__uint_as_float(r[e + 3]), sc2, -mb));
               }
-              m_run = m_new;
-            } else {
-              m_run = fmaxf(m_run, cm);
+              l_run = l_run * ex2((m_run - m_new) * sc2) + ((a0 + a1) + (a2 + a3));
             }
+            m_run = m_new;
+          } else {
+            m_run = fmaxf(m_run, cm);
           }
         }
         tc_fence_before();
@@ -311,9 +324,11 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
         if (lane == 0) mbar_arrive(&s_empty[buf]);
       }
       const float inv_l = exact ? (1.0f / l_run) : 1.0f;
-      float l_fast = 0.f;
+      const float mb2 = m_run * sc2;
+      float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lf3 = 0.f;
       const float mrow = blend ? p.mask[static_cast<long long>(fc) * p.S_q + min(q, p.S_q - 1)] : 1.f;
       const float* xe = p.xedit;
+      const bool row_ops = row_mode == FZ_ATTN_CROSSEDIT || (p.acc && edited);
       // ------------------------------ pass 2: probabilities -> P tile (-> cache) ------------------------------
       for (int b = 0; b < n_blocks; ++b, ++g) {
         const int buf = g & 1, pb = b & 1;
@@ -328,22 +343,29 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
         for (int a = 0; a < na; ++a) {
           const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
           uint8_t* prow = pbuf + a * kAtomBytes + row * 128;
-#pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + c, r);
-            tmem_ld_wait();
-            float pv[32];
+          uint32_t r[64];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+          tmem_ld_wait();
+          if (ai.valid < 64) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float s = (c + e < ai.valid) ? __uint_as_float(r[e]) * p.scale_log2 : -INFINITY;
-              pv[e] = ex2(s - m_run) * inv_l;
-            }
-            if (!exact) {
+            for (int e = 0; e < 64; ++e)
+              if (e >= ai.valid) r[e] = 0xff800000u;
+          }
+          float* pv = reinterpret_cast<float*>(r);
+          if (exact) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) l_fast += pv[e];
-            }
-            if (row_mode == FZ_ATTN_CROSSEDIT || (p.acc && edited)) {
+            for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2)) * inv_l;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
+          }
+          if (row_ops) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              float* pc = pv + c;
               // key index n = ai.k0 + c + e (single slot).  cur = fp16(p); optional running sum; optional edit (in fp32, one rounding)
               const int n0 = ai.k0 + c;
               const long long rbase = ((static_cast<long long>(fc) * p.heads + head) * p.S_q + min(q, p.S_q - 1));
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
                     uint4 v = *reinterpret_cast<uint4*>(ap + e);
                     __half* hv = reinterpret_cast<__half*>(&v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(__half2float(hv[j]) + __half2float(__float2half_rn(pv[e + j])));
+                    for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(__half2float(hv[j]) + __half2float(__float2half_rn(pc[e + j])));
                     *reinterpret_cast<uint4*>(ap + e) = v;
                   }
                 }
@@ -384,7 +406,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
                 for (int e = 0; e < 32; ++e) {
                   const int n = n0 + e;
                   if (n < p.keys_per_slot) {
-                    const float cur = __half2float(__float2half_rn(pv[e]));
+                    const float cur = __half2float(__float2half_rn(pc[e]));
                     float R;
                     if (xmode == 1) R = rr[e];
                     else {
@@ -395,22 +417,22 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
                     }
                     R *= __ldg(x_eq + n);
                     const float al = __ldg(x_alpha + n);
-                    pv[e] = R * al + (1.f - al) * cur;
+                    pc[e] = R * al + (1.f - al) * cur;
                   }
                 }
               }
             }
-            // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
+          }
+          // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              uint4 v;
-              v.x = pack_half2(pv[e + 0], pv[e + 1]);
-              v.y = pack_half2(pv[e + 2], pv[e + 3]);
-              v.z = pack_half2(pv[e + 4], pv[e + 5]);
-              v.w = pack_half2(pv[e + 6], pv[e + 7]);
-              const int j = (c + e) >> 3;
-              *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
-            }
+          for (int e = 0; e < 64; e += 8) {
+            uint4 v;
+            v.x = pack_half2(pv[e + 0], pv[e + 1]);
+            v.y = pack_half2(pv[e + 2], pv[e + 3]);
+            v.z = pack_half2(pv[e + 4], pv[e + 5]);
+            v.w = pack_half2(pv[e + 6], pv[e + 7]);
+            const int j = e >> 3;
+            *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
           }
           if (blend) {
             if (mrow == 0.f) {
@@ -439,7 +461,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
           mbar_arrive(&p_full[pb]);
         }
       }
-      if (!exact) l_run = l_fast;
+      if (!exact) l_run = (lf0 + lf1) + (lf2 + lf3);
     }
     // ------------------------------ epilogue: O (TMEM) -> fp16 -> global ------------------------------
     mbar_wait(o_full, 0);

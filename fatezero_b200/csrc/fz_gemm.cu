@@ -333,23 +333,26 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   return FZ_OK;
 }
 
-static int pick_block_n(int gemm_cols, int mode, int forced) {
+static int pick_block_n(int gemm_cols, int mode, int forced, int m_tiles) {
   if (forced > 0) return forced;
   static const int cands[] = {256, 160, 128, 64, 32, 16};
   if (mode == FZ_EPI_GEGLU) return (gemm_cols % 256 == 0) ? 256 : ((gemm_cols % 160 == 0) ? 160 : ((gemm_cols % 128 == 0) ? 128 : ((gemm_cols % 64 == 0) ? 64 : 32)));
+  // cost model: a tile costs ~ BLOCK_N MMA columns (+ a fixed part), tiles run in waves of one per SM.
+  const int sms = num_sms();
   int best = 16;
   double best_cost = 1e30;
   for (int bn : cands) {
-    const int tiles = (gemm_cols + bn - 1) / bn;
-    // cost ~ MMA columns issued, with a mild penalty for narrow tiles (more A re-reads, more smem traffic per flop)
-    const double cost = static_cast<double>(tiles) * bn * (1.0 + 24.0 / bn);
+    const long long n_tiles = (gemm_cols + bn - 1) / bn;
+    const long long tiles = n_tiles * m_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 24.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
 static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cudaStream_t stream) {
-  const int bn = pick_block_n(gemm_cols, p.mode, forced_bn);
+  const int bn = pick_block_n(gemm_cols, p.mode, forced_bn, p.m_tiles);
   p.n_tiles = (gemm_cols + bn - 1) / bn;
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);
@@ -403,7 +406,8 @@ extern "C" int fz_gemm_f16(const void* A, long long lda, const void* W, long lon
   }
   const int rc0 = fill_epilogue(p, epi, M, N);
   if (rc0) return rc0;
-  const int bn = pick_block_n(N, p.mode, force_block_n);
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int bn = pick_block_n(N, p.mode, force_block_n, p.m_tiles);
   {
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 1};
     uint64_t strides[2] = {static_cast<uint64_t>(ldw), static_cast<uint64_t>(ldw) * N};
@@ -464,7 +468,9 @@ extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, 
       p.tap_off[t][4] = py;
     }
   }
-  const int bn = pick_block_n(Cout, p.mode, force_block_n);
+  p.rows_per_tile = bw * bh * bn_img;
+  p.m_tiles = M / p.rows_per_tile;
+  const int bn = pick_block_n(Cout, p.mode, force_block_n, p.m_tiles);
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9};
     uint64_t strides[2] = {(uint64_t)Cin, (uint64_t)Cin * Cout};
@@ -502,7 +508,9 @@ extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW,
   }
   p.a_rank = 4;
   for (int t = 0; t < 3; ++t) { p.tap_off[t][2] = t - 1; }
-  const int bn = pick_block_n(Cout, p.mode, force_block_n);
+  p.rows_per_tile = bp * bf;
+  p.m_tiles = M / p.rows_per_tile;
+  const int bn = pick_block_n(Cout, p.mode, force_block_n, p.m_tiles);
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 3};
     uint64_t strides[2] = {(uint64_t)Cin, (uint64_t)Cin * Cout};

@@ -20,6 +20,18 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item(), (a - b).abs().max().item()
 
 
+def robust_rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    d = (a - b).abs().reshape(-1)
+    q = torch.quantile(d, 0.99).item()
+    return q / (b.abs().max().item() + 1e-12), q
+
+
+def outlier_frac(a, b, thr=0.05):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs() > thr * b.abs().max()).float().mean().item()
+
+
 @pytest.mark.parametrize("unet_name,mc,frames,size", [
     ("mini", dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128), 3, 32),
     ("mini", dict(lora=160), 2, 32),
@@ -63,9 +75,15 @@ def test_case_vs_oracle_and_golden(name, report):
     prod = run_product_case(case)
     orc = run_oracle_case(case)
     r_inv, a_inv = rel(prod["inv_latents"], orc["inv_latents"])
-    r_ed, a_ed = rel(prod["edit_latents"][-1], orc["edit_latents"][-1])
-    per_step = [rel(prod["edit_latents"][i], orc["edit_latents"][i])[0] for i in range(case["steps"])]
-    report[f"{name}_vs_oracle"] = dict(inv_rel=r_inv, inv_abs=a_inv, edit_rel=r_ed, edit_abs=a_ed, edit_rel_per_step=per_step)
+    blend = bool(case["p2p"].get("blend_words"))
+    # thresholded blend masks can flip single pixels between an fp16 and an fp32 run (values within rounding of th); a flipped
+    # pixel moves by O(1), so blend cases are judged on the 99th percentile + the fraction of such outliers instead of max|d|.
+    r_ed, a_ed = (robust_rel if blend else rel)(prod["edit_latents"][-1], orc["edit_latents"][-1])
+    per_step = [(robust_rel if blend else rel)(prod["edit_latents"][i], orc["edit_latents"][i])[0] for i in range(case["steps"])]
+    outl = outlier_frac(prod["edit_latents"][-1], orc["edit_latents"][-1])
+    report[f"{name}_vs_oracle"] = dict(inv_rel=r_inv, inv_abs=a_inv, edit_rel=r_ed, edit_abs=a_ed, edit_rel_per_step=per_step,
+                                       outlier_frac=outl, max_rel=rel(prod["edit_latents"][-1], orc["edit_latents"][-1])[0])
+    assert outl < 2e-2
     # stored inversion maps of step 0 against the oracle's
     store = prod["pipe"].store_controller
     worst = 0.0
@@ -80,7 +98,7 @@ def test_case_vs_oracle_and_golden(name, report):
     if os.path.exists(gpath):
         g = torch.load(gpath)
         rg_inv, _ = rel(prod["inv_latents"], g["inv_latents"])
-        rg_ed, ag_ed = rel(prod["edit_latents"][-1], g["edit_latents"][-1])
+        rg_ed, ag_ed = (robust_rel if blend else rel)(prod["edit_latents"][-1], g["edit_latents"][-1])
         report[f"{name}_vs_golden"] = dict(inv_rel=rg_inv, edit_rel=rg_ed, edit_abs=ag_ed)
         assert rg_inv < 2e-2 and rg_ed < 8e-2
         if "mask_list" in g and prod["result"]["mask_list"]:
