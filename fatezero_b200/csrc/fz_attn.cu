@@ -15,7 +15,8 @@
 // reproduced exactly at its rounding point; rows that are neither stored nor edited use the cheaper "max only" first pass and
 // normalise O at the end.
 //
-// CTA = 128 query rows of one (frame, head); 6 warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue (1 row per thread).
+// CTA = 128 query rows of one (frame, head); 10 warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = two softmax / epilogue warpgroups
+// (1 row per thread each; warpgroup w handles key blocks b with b % 2 == w so two warps per scheduler hide MUFU / TMEM latencies).
 // TMEM: S double buffer (2 x 128 cols) + O (<= 192 cols).  smem: Q tile, a ring of K / V^T atoms, P double buffer (+ base P).
 #include "fz_common.cuh"
 
@@ -73,13 +74,18 @@ struct AtomInfo {
 };
 __device__ __forceinline__ AtomInfo atom_info(const AttnParams& p, int atoms_per_slot, int A) {
   AtomInfo a;
-  a.slot = A / atoms_per_slot;
-  a.k0 = (A % atoms_per_slot) * 64;
+  if (p.n_slots == 1) {
+    a.slot = 0;
+    a.k0 = A * 64;
+  } else {
+    a.slot = A / atoms_per_slot;
+    a.k0 = (A - a.slot * atoms_per_slot) * 64;
+  }
   a.valid = min(64, p.keys_per_slot - a.k0);
   return a;
 }
 
-__global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -268,7 +274,9 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
     const int q = q0 + row;
     const bool row_ok = q < p.S_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const int st = threadIdx.x - 64;  // 0..127 among the softmax threads
+    const int wg = (warp - 2) >> 2;            // softmax warpgroup: handles key blocks with (b & 1) == wg
+    const int st = (threadIdx.x - 64) & 127;   // 0..127 within the warpgroup
+    float* xchg = reinterpret_cast<float*>(bars + 32);  // [2 warpgroups][128 rows][2] exchange buffer
     float m_run = -INFINITY, l_run = 0.f;
     int g = 0;
     if (!replace) {
@@ -276,6 +284,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
       // m_run tracks the max of the RAW scores (scale > 0); exponent arguments are formed with one FFMA: s*scale_log2 - m*scale_log2
       const float sc2 = p.scale_log2;
       for (int b = 0; b < n_blocks; ++b, ++g) {
+        if ((b & 1) != wg) continue;
         const int buf = g & 1;
         mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc_fence_after();
@@ -323,6 +332,17 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);
       }
+      // merge the two warpgroups' running (max, sum)
+      xchg[(wg * 128 + row) * 2 + 0] = m_run;
+      xchg[(wg * 128 + row) * 2 + 1] = l_run;
+      named_bar_sync(3, 256);
+      {
+        const float m_o = xchg[((wg ^ 1) * 128 + row) * 2 + 0], l_o = xchg[((wg ^ 1) * 128 + row) * 2 + 1];
+        const float m_new = fmaxf(m_run, m_o);
+        if (exact) l_run = l_run * ex2((m_run - m_new) * sc2) + l_o * ex2((m_o - m_new) * sc2);
+        m_run = m_new;
+      }
+      named_bar_sync(3, 256);
       const float inv_l = exact ? (1.0f / l_run) : 1.0f;
       const float mb2 = m_run * sc2;
       float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lf3 = 0.f;
@@ -331,12 +351,13 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
       const bool row_ops = row_mode == FZ_ATTN_CROSSEDIT || (p.acc && edited);
       // ------------------------------ pass 2: probabilities -> P tile (-> cache) ------------------------------
       for (int b = 0; b < n_blocks; ++b, ++g) {
+        if ((b & 1) != wg) continue;
         const int buf = g & 1, pb = b & 1;
         mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc_fence_after();
-        if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<1>();  // P buffer pb was read by the store issued 2 blocks ago
+        if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<0>();  // this warpgroup's P buffer was read by its previous store
         mbar_wait(&p_empty[pb], ((b >> 1) & 1) ^ 1);
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + wg, 128);
         if (blend) { mbar_wait(base_full, b & 1); }
         uint8_t* pbuf = s_p + pb * 2 * kAtomBytes;
         const int na = min(2, n_atoms - 2 * b);
@@ -449,7 +470,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
           if (blend) mbar_arrive(base_empty);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + wg, 128);
         if (st == 0) {
           if (row_mode == FZ_ATTN_STORE) {
             for (int a = 0; a < na; ++a) {
@@ -461,7 +482,12 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
           mbar_arrive(&p_full[pb]);
         }
       }
-      if (!exact) l_run = (lf0 + lf1) + (lf2 + lf3);
+      if (!exact) {
+        l_run = (lf0 + lf1) + (lf2 + lf3);
+        xchg[(wg * 128 + row) * 2] = l_run;
+        named_bar_sync(3, 256);
+        l_run += xchg[((wg ^ 1) * 128 + row) * 2];
+      }
     }
     // ------------------------------ epilogue: O (TMEM) -> fp16 -> global ------------------------------
     mbar_wait(o_full, 0);
@@ -469,7 +495,7 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const __grid_constant__ At
     const float o_scale = (!replace && !exact) ? (1.0f / l_run) : 1.0f;
     __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + min(q, p.S_q - 1)) * p.ldo + head * p.d;
 #pragma unroll 1
-    for (int c = 0; c < p.d_pad; c += 16) {
+    for (int c = wg * 16; c < p.d_pad; c += 32) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_o + lane_addr + c, r);
       tmem_ld_wait();
@@ -566,7 +592,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
   }
   // shared memory plan
   const int stage_bytes = std::max(kAtomBytes, (p.d_pad * 128 + 1023) / 1024 * 1024);
-  const int fixed = p.nd * kAtomBytes + 4 * kAtomBytes + (a->row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0) + 1024 + 512;
+  const int fixed = p.nd * kAtomBytes + 4 * kAtomBytes + (a->row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0) + 1024 + 3072;
   int stages = 6;
   while (stages > 2 && fixed + stages * stage_bytes > 225 * 1024) --stages;
   FZ_CHECK_ARG(fixed + stages * stage_bytes <= 227 * 1024, "fz_attention: shared memory plan does not fit (d=%d)", a->d);
@@ -578,7 +604,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     configured = smem;
   }
   dim3 grid((a->S_q + 127) / 128, a->heads, a->BF);
-  attn_kernel<<<grid, 192, smem, stream>>>(p);
+  attn_kernel<<<grid, 320, smem, stream>>>(p);
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }

@@ -34,16 +34,18 @@ struct alignas(16) Half8 {
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxSlots = 4;
 
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, int frames_per_stat,
-                                                             int TX, int slots, int px_per_cta, double* __restrict__ sums) {
-  __shared__ float s_sum[64], s_sq[64];
+// Statistics pass: every CTA reduces its pixel chunk of one image to per-group partial (sum, sumsq) WITHOUT atomics
+// (v0 used ~4k contended shared-memory atomics per CTA): registers -> smem [TY][C] -> per channel -> per group -> partial[nb][chunk][g].
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, int TX, int slots,
+                                                             int px_per_cta, float2* __restrict__ partial) {
+  extern __shared__ float gn_smem[];  // [TY][C] sums, [TY][C] sumsq
   const int nb = blockIdx.y;
   const int CV = C / 8;
   const int cpg = C / G;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = kGnThreads / TX;
-  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
+  float* s_sum = gn_smem;
+  float* s_sq = gn_smem + TY * C;
   float acc[kGnMaxSlots][8], acc2[kGnMaxSlots][8];
 #pragma unroll
   for (int s = 0; s < kGnMaxSlots; ++s)
@@ -53,11 +55,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
   const int p1 = min(HW, p0 + px_per_cta);
   if (ty < TY) {
     const __half* xb = x + (static_cast<long long>(nb) * HW) * C;
+#pragma unroll 2
     for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
       for (int s = 0; s < kGnMaxSlots; ++s) {
         const int cv = tx + s * TX;
-        if (s < slots && cv < CV) {
+        if (s < slots) {
           const Half8 h = *reinterpret_cast<const Half8*>(xb + static_cast<long long>(p) * C + cv * 8);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -71,62 +74,93 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
 #pragma unroll
     for (int s = 0; s < kGnMaxSlots; ++s) {
       const int cv = tx + s * TX;
-      if (s < slots && cv < CV) {
+      if (s < slots) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int g = (cv * 8 + e) / cpg;
-          atomicAdd(&s_sum[g], acc[s][e]);
-          atomicAdd(&s_sq[g], acc2[s][e]);
+          s_sum[ty * C + cv * 8 + e] = acc[s][e];
+          s_sq[ty * C + cv * 8 + e] = acc2[s][e];
         }
       }
     }
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    float a = 0.f, b = 0.f;
+    for (int t = 0; t < TY; ++t) { a += s_sum[t * C + c]; b += s_sq[t * C + c]; }
+    s_sum[c] = a;
+    s_sq[c] = b;
+  }
+  __syncthreads();
   if (threadIdx.x < G) {
-    double* dst = sums + (static_cast<long long>(nb / frames_per_stat) * G + threadIdx.x) * 2;
-    atomicAdd(dst, static_cast<double>(s_sum[threadIdx.x]));
-    atomicAdd(dst + 1, static_cast<double>(s_sq[threadIdx.x]));
+    float a = 0.f, b = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += s_sum[c]; b += s_sq[c]; }
+    partial[(static_cast<long long>(nb) * gridDim.x + blockIdx.x) * G + threadIdx.x] = make_float2(a, b);
   }
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, int C, int G,
-                                                             int frames_per_stat, int TX, int slots, int px_per_cta,
-                                                             const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                             int frames_per_stat, int TX, int slots, int px_per_cta, int chunks,
+                                                             const float2* __restrict__ partial, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int silu) {
+  __shared__ double s_red[kGnThreads][2];
+  __shared__ float s_mean[64], s_rstd[64];
   const int nb = blockIdx.y;
   const int CV = C / 8;
   const int cpg = C / G;
+  // group statistics of this image's stat set: sum the partials of its frames_per_stat images x chunks (fp64)
+  {
+    const int first_nb = (nb / frames_per_stat) * frames_per_stat;
+    const int n_part = frames_per_stat * chunks;  // partials per group, contiguous per image: [(nb*chunks + chunk)*G + g]
+    const int g = threadIdx.x % G, lane_j = threadIdx.x / G, n_j = kGnThreads / G;
+    double a = 0.0, b = 0.0;
+    if (lane_j < n_j) {
+      for (int i = lane_j; i < n_part; i += n_j) {
+        const float2 v = partial[(static_cast<long long>(first_nb) * chunks + i) * G + g];
+        a += v.x;
+        b += v.y;
+      }
+    }
+    s_red[threadIdx.x][0] = a;
+    s_red[threadIdx.x][1] = b;
+    __syncthreads();
+    if (threadIdx.x < G) {
+      double sa = 0.0, sb = 0.0;
+      for (int j = 0; j < n_j; ++j) { sa += s_red[j * G + threadIdx.x][0]; sb += s_red[j * G + threadIdx.x][1]; }
+      const double cnt = static_cast<double>(cpg) * HW * frames_per_stat;
+      const double mean = sa / cnt;
+      double var = sb / cnt - mean * mean;
+      if (var < 0) var = 0;
+      s_mean[threadIdx.x] = static_cast<float>(mean);
+      s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+  }
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = kGnThreads / TX;
   if (ty >= TY) return;
-  const double cnt = static_cast<double>(cpg) * HW * frames_per_stat;
   float sc[kGnMaxSlots][8], sh[kGnMaxSlots][8];
 #pragma unroll
   for (int s = 0; s < kGnMaxSlots; ++s) {
     const int cv = tx + s * TX;
-    if (s < slots && cv < CV) {
+    if (s < slots) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = cv * 8 + e;
         const int g = c / cpg;
-        const double* src = sums + (static_cast<long long>(nb / frames_per_stat) * G + g) * 2;
-        const double mean = src[0] / cnt;
-        double var = src[1] / cnt - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-        sc[s][e] = rstd * gamma[c];
-        sh[s][e] = beta[c] - static_cast<float>(mean) * rstd * gamma[c];
+        sc[s][e] = s_rstd[g] * gamma[c];
+        sh[s][e] = beta[c] - s_mean[g] * s_rstd[g] * gamma[c];
       }
     }
   }
   const int p0 = blockIdx.x * px_per_cta;
   const int p1 = min(HW, p0 + px_per_cta);
   const long long base = (static_cast<long long>(nb) * HW) * C;
+#pragma unroll 2
   for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
     for (int s = 0; s < kGnMaxSlots; ++s) {
       const int cv = tx + s * TX;
-      if (s < slots && cv < CV) {
+      if (s < slots) {
         const long long off = base + static_cast<long long>(p) * C + cv * 8;
         const Half8 h = *reinterpret_cast<const Half8*>(x + off);
         Half8 o;
@@ -160,52 +194,73 @@ static void gn_geometry(int C, int HW, int NB, int* TX, int* slots, int* px_per_
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // C <= 8*32*8 = 2048
 
+constexpr int kLnRows = 2;  // rows per warp in flight (memory-level parallelism)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long M, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kLnRows;
+  if (row0 >= M) return;
   const int CV = C / 8;
-  Half8 buf[kLnMaxVec];
-  float sum = 0.f;
+  Half8 buf[kLnRows][kLnMaxVec];
+  float sum[kLnRows], sq[kLnRows];
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
-      buf[i] = *reinterpret_cast<const Half8*>(x + row * C + cv * 8);
+  for (int r = 0; r < kLnRows; ++r) {
+    sum[r] = 0.f;
+    const long long row = min(row0 + r, M - 1);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += __half2float(buf[i].v[e]);
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int cv = lane + i * 32;
+      if (cv < CV) buf[r][i] = *reinterpret_cast<const Half8*>(x + row * C + cv * 8);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
+  for (int r = 0; r < kLnRows; ++r) {
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (lane + i * 32 < CV) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = __half2float(buf[i].v[e]) - mean;
-        sq += d * d;
+        for (int e = 0; e < 8; ++e) sum[r] += __half2float(buf[r][i].v[e]);
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
+  for (int r = 0; r < kLnRows; ++r) {
+    const float mean = sum[r] / C;
+    sq[r] = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int cv = lane + i * 32;
-    if (cv < CV) {
-      Half8 o;
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (lane + i * 32 < CV) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cv * 8 + e;
-        o.v[e] = __float2half_rn((__half2float(buf[i].v[e]) - mean) * rstd * gamma[c] + beta[c]);
+        for (int e = 0; e < 8; ++e) {
+          const float d = __half2float(buf[r][i].v[e]) - mean;
+          sq[r] += d * d;
+        }
       }
-      *reinterpret_cast<Half8*>(y + row * C + cv * 8) = o;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
+  }
+#pragma unroll
+  for (int r = 0; r < kLnRows; ++r) {
+    const long long row = row0 + r;
+    if (row >= M) break;
+    const float mean = sum[r] / C;
+    const float rstd = rsqrtf(sq[r] / C + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int cv = lane + i * 32;
+      if (cv < CV) {
+        Half8 o;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o.v[e] = __float2half_rn((__half2float(buf[r][i].v[e]) - mean) * rstd * gg[e] + bb[e]);
+        *reinterpret_cast<Half8*>(y + row * C + cv * 8) = o;
+      }
     }
   }
 }
@@ -534,13 +589,19 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
   int TX, slots, ppc, chunks;
   gn_geometry(C, HW, NB, &TX, &slots, &ppc, &chunks);
   FZ_CHECK_ARG(slots <= kGnMaxSlots, "fz_groupnorm: C=%d too large", C);
-  const size_t ws_bytes = static_cast<size_t>(NB / frames_per_stat) * groups * 2 * sizeof(double);
-  FZ_CUDA(cudaMemsetAsync(workspace_f64, 0, ws_bytes, stream));
+  FZ_CHECK_ARG(static_cast<size_t>(NB) * chunks * groups * sizeof(float2) <= (1u << 20), "fz_groupnorm: workspace (1 MiB) too small");
+  const int TY = kGnThreads / TX;
+  const size_t smem = static_cast<size_t>(2) * TY * C * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
   dim3 grid(chunks, NB);
-  gn_stats_kernel<<<grid, kGnThreads, 0, stream>>>(static_cast<const __half*>(x), HW, C, groups, frames_per_stat, TX, slots, ppc,
-                                                   static_cast<double*>(workspace_f64));
+  float2* partial = static_cast<float2*>(workspace_f64);
+  gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(static_cast<const __half*>(x), HW, C, groups, TX, slots, ppc, partial);
   gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(y), HW, C, groups, frames_per_stat, TX,
-                                                   slots, ppc, static_cast<const double*>(workspace_f64), gamma, beta, eps, silu);
+                                                   slots, ppc, chunks, partial, gamma, beta, eps, silu);
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
@@ -549,7 +610,7 @@ extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, cons
                                 cudaStream_t stream) {
   FZ_CHECK_ARG(x && y && gamma && beta, "fz_layernorm: null pointer");
   FZ_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * kLnMaxVec, "fz_layernorm: C=%d unsupported", C);
-  layernorm_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(y), M, C, gamma,
+  layernorm_kernel<<<static_cast<unsigned>((M + 8 * kLnRows - 1) / (8 * kLnRows)), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(y), M, C, gamma,
                                                                            beta, eps);
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;

@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
     }
   } else {
     // ===================== epilogue warps =====================
+    // Straight-line fast path per 32-column chunk (all option tests are warp-uniform and hoisted out of the element loops):
+    // the v0 epilogue spent ~46 instructions per output element on per-element bound / option branches (ncu: 7 % tensor pipe
+    // on K=320 GEMMs); edge tiles fall back to the generic masked path.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row_in_tile = quad * 32 + lane;
     int local = 0;
@@ -199,25 +202,40 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
             }
             tmem_ld_wait();
             const int ocol0 = nt * HALF + c;
-            if (row_ok) {
+            if (row_ok && ocol0 + CH <= p.N) {
+              float xv[CH], gv[CH];
 #pragma unroll
-              for (int j = 0; j < CH; j += 8) {
-                __align__(16) __half hv[8];
+              for (int e = 0; e < CH; ++e) { xv[e] = __uint_as_float(xa[e]); gv[e] = __uint_as_float(ga[e]); }
+              if (p.bias) {
+                const float4* bx = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c);
+                const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + HALF + c);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float xv = __uint_as_float(xa[j + e]), gv = __uint_as_float(ga[j + e]);
-                  if (p.bias) {
-                    xv += p.bias[nt * BLOCK_N + c + j + e];
-                    gv += p.bias[nt * BLOCK_N + HALF + c + j + e];
-                  }
-                  hv[e] = __float2half_rn(xv * gelu_erf(gv));
+                for (int j = 0; j < CH / 4; ++j) {
+                  const float4 a = __ldg(bx + j), b = __ldg(bg + j);
+                  xv[4 * j] += a.x; xv[4 * j + 1] += a.y; xv[4 * j + 2] += a.z; xv[4 * j + 3] += a.w;
+                  gv[4 * j] += b.x; gv[4 * j + 1] += b.y; gv[4 * j + 2] += b.z; gv[4 * j + 3] += b.w;
                 }
-                const int oc = ocol0 + j;
-                if (oc + 8 <= p.N) {
-                  *reinterpret_cast<uint4*>(p.out + m * p.ldo + oc) = *reinterpret_cast<const uint4*>(hv);
-                } else {
-                  for (int e = 0; e < 8; ++e)
-                    if (oc + e < p.N) p.out[m * p.ldo + oc + e] = hv[e];
+              }
+              uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + ocol0);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint4 o;
+                __half2 h0 = __floats2half2_rn(xv[8 * j + 0] * gelu_erf(gv[8 * j + 0]), xv[8 * j + 1] * gelu_erf(gv[8 * j + 1]));
+                __half2 h1 = __floats2half2_rn(xv[8 * j + 2] * gelu_erf(gv[8 * j + 2]), xv[8 * j + 3] * gelu_erf(gv[8 * j + 3]));
+                __half2 h2 = __floats2half2_rn(xv[8 * j + 4] * gelu_erf(gv[8 * j + 4]), xv[8 * j + 5] * gelu_erf(gv[8 * j + 5]));
+                __half2 h3 = __floats2half2_rn(xv[8 * j + 6] * gelu_erf(gv[8 * j + 6]), xv[8 * j + 7] * gelu_erf(gv[8 * j + 7]));
+                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                op[j] = o;
+              }
+            } else if (row_ok) {
+#pragma unroll
+              for (int e = 0; e < CH; ++e) {
+                const int oc = ocol0 + e;
+                if (oc < p.N) {
+                  float xv = __uint_as_float(xa[e]), gv = __uint_as_float(ga[e]);
+                  if (p.bias) { xv += p.bias[nt * BLOCK_N + c + e]; gv += p.bias[nt * BLOCK_N + HALF + c + e]; }
+                  p.out[m * p.ldo + oc] = __float2half_rn(xv * gelu_erf(gv));
                 }
               }
             }
@@ -225,6 +243,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
         }
       } else {
         constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+        const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += CH) {
           uint32_t acc[CH];
@@ -232,60 +251,92 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
           else tmem_ld_32x32b_x16(t_row + c, reinterpret_cast<uint32_t(&)[16]>(acc));
           tmem_ld_wait();
           const int col0 = nt * BLOCK_N + c;
-          if (row_ok && col0 < p.N) {
-            const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
-            if (col0 >= p.vt_col_start) {
-              // V^T store: out_vt[((bf*heads + h)*d + dd)*S + s]; lanes = consecutive s -> 64-byte coalesced segments
-              const long long bf = m / p.vt_S;
-              const int s = static_cast<int>(m % p.vt_S);
+          if (!row_ok || col0 >= p.N) continue;
+          if (col0 + CH <= p.N && col0 + CH <= p.vt_col_start) {
+            // ---------------- fast path: full chunk, row-major output ----------------
+            float v[CH];
 #pragma unroll
-              for (int e = 0; e < CH; ++e) {
-                const int col = col0 + e;
-                if (col < p.N) {
-                  float v = __uint_as_float(acc[e]);
-                  if (p.bias) v += p.bias[col];
-                  const int cv = col - p.vt_col_start;
-                  const int h = cv / p.vt_d, dd = cv % p.vt_d;
-                  p.out_vt[((bf * p.vt_heads + h) * p.vt_d + dd) * p.vt_ld + s] = __float2half_rn(v);
-                }
+            for (int e = 0; e < CH; ++e) v[e] = __uint_as_float(acc[e]);
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 b = __ldg(bp + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
-            } else {
+            }
+            if (gb) {
+              const float4* bp = reinterpret_cast<const float4*>(gb + col0);
 #pragma unroll
-              for (int j = 0; j < CH; j += 8) {
-                const int col = col0 + j;
-                if (col < p.N) {
-                  __align__(16) __half hv[8];
-                  __align__(16) __half rv[8];
-                  __align__(16) __half rv2[8];
-                  const bool full8 = col + 8 <= p.N;
-                  if (p.residual2) {
-                    if (full8) *reinterpret_cast<uint4*>(rv2) = *reinterpret_cast<const uint4*>(p.residual2 + m * p.ldr2 + col);
-                    else
-                      for (int e = 0; e < 8; ++e) rv2[e] = (col + e < p.N) ? p.residual2[m * p.ldr2 + col + e] : __half(0.f);
-                  }
-                  if (p.residual) {
-                    if (full8) *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col);
-                    else
-                      for (int e = 0; e < 8; ++e) rv[e] = (col + e < p.N) ? p.residual[m * p.ldr + col + e] : __half(0.f);
-                  }
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 b = __ldg(bp + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    float v = __uint_as_float(acc[j + e]);
-                    if (col + e < p.N) {
-                      if (p.bias) v += p.bias[col + e];
-                      if (gb) v += gb[col + e];
-                      if (p.residual) v += __half2float(rv[e]);
-                      if (p.residual2) v += __half2float(rv2[e]);
-                    }
-                    hv[e] = __float2half_rn(v);
-                  }
-                  if (full8) {
-                    *reinterpret_cast<uint4*>(p.out + m * p.ldo + col) = *reinterpret_cast<const uint4*>(hv);
-                  } else {
-                    for (int e = 0; e < 8; ++e)
-                      if (col + e < p.N) p.out[m * p.ldo + col + e] = hv[e];
-                  }
-                }
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 r = rp[j];
+                const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+              }
+            }
+            if (p.residual2) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual2 + m * p.ldr2 + col0);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 r = rp[j];
+                const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint4 o;
+              __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+              __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+              o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+              op[j] = o;
+            }
+          } else if (col0 >= p.vt_col_start) {
+            // ---------------- V^T store: out_vt[((bf*heads + h)*d + dd)*ld + s]; lanes = consecutive s -> 64-byte segments ----------------
+            const long long bf = m / p.vt_S;
+            const int s = static_cast<int>(m % p.vt_S);
+            const int cv0 = col0 - p.vt_col_start;
+            int h = cv0 / p.vt_d, dd = cv0 % p.vt_d;
+            __half* vbase = p.out_vt + (bf * p.vt_heads) * static_cast<long long>(p.vt_d) * p.vt_ld + s;
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+              if (col0 + e < p.N) {
+                float v = __uint_as_float(acc[e]);
+                if (p.bias) v += p.bias[col0 + e];
+                vbase[(static_cast<long long>(h) * p.vt_d + dd) * p.vt_ld] = __float2half_rn(v);
+              }
+              if (++dd == p.vt_d) { dd = 0; ++h; }
+            }
+          } else {
+            // ---------------- generic masked path (right-edge tiles, chunks straddling vt_col_start) ----------------
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+              const int col = col0 + e;
+              if (col >= p.N) continue;
+              float v = __uint_as_float(acc[e]);
+              if (p.bias) v += p.bias[col];
+              if (col >= p.vt_col_start) {
+                const long long bf = m / p.vt_S;
+                const int s = static_cast<int>(m % p.vt_S);
+                const int cv = col - p.vt_col_start;
+                p.out_vt[((bf * p.vt_heads + cv / p.vt_d) * p.vt_d + cv % p.vt_d) * p.vt_ld + s] = __float2half_rn(v);
+              } else {
+                if (gb) v += gb[col];
+                if (p.residual) v += __half2float(p.residual[m * p.ldr + col]);
+                if (p.residual2) v += __half2float(p.residual2[m * p.ldr2 + col]);
+                p.out[m * p.ldo + col] = __float2half_rn(v);
               }
             }
           }

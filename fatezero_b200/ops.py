@@ -139,7 +139,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    ws = _workspace(x.device, (NB // frames_per_stat) * groups * 16)
+    ws = _workspace(x.device, 1 << 20)  # per-(image, chunk, group) partial sums
     _lib.call("fz_groupnorm_nhwc_f16", _p(x), _p(out), NB, HW, Cc, groups, frames_per_stat, _p(gamma), _p(beta), float(eps), int(silu),
               _p(ws), _stream())
     return out
