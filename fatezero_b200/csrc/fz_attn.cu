@@ -85,6 +85,10 @@ __device__ __forceinline__ AtomInfo atom_info(const AttnParams& p, int atoms_per
   return a;
 }
 
+// Pipeline granularity = one ATOM of 64 keys.  TMEM: 4 S buffers of 64 columns ([0,256)) + O at column 256.  smem: 4 P buffers
+// (128 rows x 64 keys, swizzled) + 2 cached-P ("base") buffers for BLEND.  Softmax warpgroup w owns the atoms with (A & 1) == w,
+// hence S buffers {w, w+2} (mod pass offset), P buffers {w, w+2} and base buffer w: every mbarrier is waited on by one agent in
+// program order, so parity waits can never run two phases ahead.
 __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,43 +105,45 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
 
   uint8_t* s_q = smem;
   uint8_t* s_ring = s_q + p.nd * kAtomBytes;
-  uint8_t* s_p = s_ring + p.ring_stages * p.ring_stage_bytes;
-  uint8_t* s_pbase = s_p + 2 * 2 * kAtomBytes;
+  uint8_t* s_p = s_ring + p.ring_stages * p.ring_stage_bytes;  // 4 x 16 KiB
+  uint8_t* s_pbase = s_p + 4 * kAtomBytes;                     // 2 x 16 KiB (BLEND only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_pbase + (p.row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0));
-  uint64_t* ring_full = bars;
-  uint64_t* ring_empty = bars + 8;
-  uint64_t* q_full = bars + 16;
-  uint64_t* s_full = bars + 17;   // [2]
-  uint64_t* s_empty = bars + 19;  // [2]
-  uint64_t* p_full = bars + 21;   // [2]
-  uint64_t* p_empty = bars + 23;  // [2]
-  uint64_t* o_full = bars + 25;
-  uint64_t* base_full = bars + 26;
-  uint64_t* base_empty = bars + 27;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* ring_full = bars;        // [12]
+  uint64_t* ring_empty = bars + 12;  // [12]
+  uint64_t* q_full = bars + 24;
+  uint64_t* s_full = bars + 25;      // [4]
+  uint64_t* s_empty = bars + 29;     // [4]
+  uint64_t* p_full = bars + 33;      // [4]
+  uint64_t* p_empty = bars + 37;     // [4]
+  uint64_t* o_full = bars + 41;
+  uint64_t* base_full = bars + 42;   // [2]
+  uint64_t* base_empty = bars + 44;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 46);
+  float* xchg = reinterpret_cast<float*>(bars + 48);  // [2 warpgroups][128 rows][2]
 
   const int atoms_per_slot = (p.keys_per_slot + 63) / 64;
   const int n_atoms = atoms_per_slot * p.n_slots;
-  const int n_blocks = (n_atoms + 1) / 2;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmVt);
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < 12; ++s) {
       mbar_init(&ring_full[s], 1);
       mbar_init(&ring_empty[s], 1);
     }
     mbar_init(q_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_empty[b], 4);
       mbar_init(&p_full[b], 1);
       mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_full, 1);
-    mbar_init(base_full, 1);
-    mbar_init(base_empty, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&base_full[b], 1);
+      mbar_init(&base_empty[b], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -153,57 +159,49 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
-      auto load_k_block = [&](int b) {
-        const int na = min(2, n_atoms - 2 * b);
+      auto load_k = [&](int A) {
+        const AtomInfo ai = atom_info(p, atoms_per_slot, A);
+        const int src = p.src_index[ai.slot][bf];
         for (int c = 0; c < p.nd; ++c) {
           mbar_wait(&ring_empty[stage], phase ^ 1);
-          uint8_t* dst = s_ring + stage * p.ring_stage_bytes;
-          mbar_expect_tx(&ring_full[stage], na * 64 * 128);
-          for (int a = 0; a < na; ++a) {
-            const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
-            tma_load_4d(dst + a * 64 * 128, &p.tmK, &ring_full[stage], c * 64, head, ai.k0, p.src_index[ai.slot][bf]);
-          }
+          mbar_expect_tx(&ring_full[stage], 64 * 128);
+          tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmK, &ring_full[stage], c * 64, head, ai.k0, src);
           advance();
         }
       };
-      auto load_v_block = [&](int b) {
-        const int na = min(2, n_atoms - 2 * b);
-        for (int a = 0; a < na; ++a) {
-          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
-          mbar_wait(&ring_empty[stage], phase ^ 1);
-          mbar_expect_tx(&ring_full[stage], p.d_pad * 128);
-          tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmVt, &ring_full[stage], ai.k0, 0, head, p.src_index[ai.slot][bf]);
-          advance();
-        }
+      auto load_v = [&](int A) {
+        const AtomInfo ai = atom_info(p, atoms_per_slot, A);
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], p.d_pad * 128);
+        tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmVt, &ring_full[stage], ai.k0, 0, head, p.src_index[ai.slot][bf]);
+        advance();
       };
-      auto load_base_block = [&](int b, uint8_t* dst, uint64_t* bar) {
-        const int na = min(2, n_atoms - 2 * b);
-        mbar_expect_tx(bar, na * kAtomBytes);
-        for (int a = 0; a < na; ++a) {
-          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
-          tma_load_5d(dst + a * kAtomBytes, &p.tmBase, bar, ai.k0, ai.slot, q0, head, fc);
-        }
+      auto load_base = [&](int A, uint8_t* dst, uint64_t* bar) {
+        const AtomInfo ai = atom_info(p, atoms_per_slot, A);
+        mbar_expect_tx(bar, kAtomBytes);
+        tma_load_5d(dst, &p.tmBase, bar, ai.k0, ai.slot, q0, head, fc);
       };
       if (!replace) {
-        // Q tile: nd atoms of [128 rows x 64 dims]
         mbar_expect_tx(q_full, p.nd * kAtomBytes);
         for (int c = 0; c < p.nd; ++c) tma_load_4d(s_q + c * kAtomBytes, &p.tmQ, q_full, c * 64, head, q0, bf);
-        for (int b = 0; b < n_blocks; ++b) load_k_block(b);  // pass 1
-        load_k_block(0);                                      // pass 2
-        for (int b = 0; b < n_blocks; ++b) {
-          if (b + 1 < n_blocks) load_k_block(b + 1);
+        for (int A = 0; A < n_atoms; ++A) load_k(A);  // pass 1
+        load_k(0);                                     // pass 2 (two S tiles of look-ahead, one per warpgroup)
+        if (n_atoms > 1) load_k(1);
+        for (int A = 0; A < n_atoms; ++A) {
+          if (A + 2 < n_atoms) load_k(A + 2);
           if (blend) {
-            mbar_wait(base_empty, ((b & 1) ^ 1));
-            load_base_block(b, s_pbase, base_full);
+            const int w = A & 1;
+            mbar_wait(&base_empty[w], ((A >> 1) & 1) ^ 1);
+            load_base(A, s_pbase + w * kAtomBytes, &base_full[w]);
           }
-          load_v_block(b);
+          load_v(A);
         }
       } else {
-        for (int b = 0; b < n_blocks; ++b) {
-          const int pb = b & 1;
-          mbar_wait(&p_empty[pb], ((b >> 1) & 1) ^ 1);
-          load_base_block(b, s_p + pb * 2 * kAtomBytes, &p_full[pb]);
-          load_v_block(b);
+        for (int A = 0; A < n_atoms; ++A) {
+          const int pb = A & 3;
+          mbar_wait(&p_empty[pb], ((A >> 2) & 1) ^ 1);
+          load_base(A, s_p + pb * kAtomBytes, &p_full[pb]);
+          load_v(A);
         }
       }
     }
@@ -214,125 +212,115 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
       const uint32_t idesc_o = umma_idesc_f16(128, p.d_pad);
-      int g = 0;  // S-buffer use counter across both passes
-      auto issue_s = [&](int b) {
-        const int buf = g & 1;
-        mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+      const uint32_t idesc_s = umma_idesc_f16(128, 64);
+      int g = 0;  // S-tile counter across both passes
+      auto issue_s = [&]() {
+        const int sb = g & 3;
+        mbar_wait(&s_empty[sb], ((g >> 2) & 1) ^ 1);
         tc_fence_after();
-        const int na = min(2, n_atoms - 2 * b);
-        const uint32_t idesc_s = umma_idesc_f16(128, na * 64);
-        const uint32_t d_tmem = tmem_base + buf * 128;
+        const uint32_t d_tmem = tmem_base + sb * 64;
         for (int c = 0; c < p.nd; ++c) {
           mbar_wait(&ring_full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(s_q + c * kAtomBytes);
-          const uint32_t sb = smem_u32(s_ring + stage * p.ring_stage_bytes);
+          const uint32_t sb_addr = smem_u32(s_ring + stage * p.ring_stage_bytes);
           const int ksteps = min(4, (p.d - c * 64 + 15) / 16);
           for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc_s, (c | k) ? 1u : 0u);
+            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb_addr + k * 32), idesc_s, (c | k) ? 1u : 0u);
           umma_commit(&ring_empty[stage]);
           advance();
         }
-        umma_commit(&s_full[buf]);
+        umma_commit(&s_full[sb]);
         ++g;
       };
-      auto issue_pv = [&](int b) {
-        const int pb = b & 1;
-        mbar_wait(&p_full[pb], (b >> 1) & 1);
+      auto issue_pv = [&](int A) {
+        const int pb = A & 3;
+        mbar_wait(&p_full[pb], (A >> 2) & 1);
         tc_fence_after();
-        const int na = min(2, n_atoms - 2 * b);
-        for (int a = 0; a < na; ++a) {
-          mbar_wait(&ring_full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(s_p + pb * 2 * kAtomBytes + a * kAtomBytes);
-          const uint32_t sb = smem_u32(s_ring + stage * p.ring_stage_bytes);
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_o, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc_o, (b | a | k) ? 1u : 0u);
-          umma_commit(&ring_empty[stage]);
-          advance();
-        }
+        mbar_wait(&ring_full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(s_p + pb * kAtomBytes);
+        const uint32_t sb_addr = smem_u32(s_ring + stage * p.ring_stage_bytes);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_o, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb_addr + k * 32), idesc_o, (A | k) ? 1u : 0u);
+        umma_commit(&ring_empty[stage]);
+        advance();
         umma_commit(&p_empty[pb]);
       };
       if (!replace) {
         mbar_wait(q_full, 0);
         tc_fence_after();
-        for (int b = 0; b < n_blocks; ++b) issue_s(b);
-        issue_s(0);
-        for (int b = 0; b < n_blocks; ++b) {
-          if (b + 1 < n_blocks) issue_s(b + 1);
-          issue_pv(b);
+        for (int A = 0; A < n_atoms; ++A) issue_s();
+        issue_s();
+        if (n_atoms > 1) issue_s();
+        for (int A = 0; A < n_atoms; ++A) {
+          if (A + 2 < n_atoms) issue_s();
+          issue_pv(A);
         }
       } else {
-        for (int b = 0; b < n_blocks; ++b) issue_pv(b);
+        for (int A = 0; A < n_atoms; ++A) issue_pv(A);
       }
       umma_commit(o_full);
     }
   } else {
-    // =========================================== softmax / epilogue warps ===========================================
+    // =========================================== softmax / epilogue warpgroups ===========================================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
     const int q = q0 + row;
     const bool row_ok = q < p.S_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const int wg = (warp - 2) >> 2;            // softmax warpgroup: handles key blocks with (b & 1) == wg
+    const int wg = (warp - 2) >> 2;            // handles atoms with (A & 1) == wg
     const int st = (threadIdx.x - 64) & 127;   // 0..127 within the warpgroup
-    float* xchg = reinterpret_cast<float*>(bars + 32);  // [2 warpgroups][128 rows][2] exchange buffer
     float m_run = -INFINITY, l_run = 0.f;
-    int g = 0;
     if (!replace) {
-      // ------------------------------ pass 1: row max (and sum when exact) ------------------------------
-      // m_run tracks the max of the RAW scores (scale > 0); exponent arguments are formed with one FFMA: s*scale_log2 - m*scale_log2
+      // ------------------------------ pass 1: row max of the raw scores (and sum of exponentials when exact) ------------------------------
       const float sc2 = p.scale_log2;
-      for (int b = 0; b < n_blocks; ++b, ++g) {
-        if ((b & 1) != wg) continue;
-        const int buf = g & 1;
-        mbar_wait(&s_full[buf], (g >> 1) & 1);
+      for (int A = wg; A < n_atoms; A += 2) {
+        const int g = A, sb = g & 3;
+        mbar_wait(&s_full[sb], (g >> 2) & 1);
         tc_fence_after();
-        const int na = min(2, n_atoms - 2 * b);
-        for (int a = 0; a < na; ++a) {
-          const int valid = atom_info(p, atoms_per_slot, 2 * b + a).valid;
-          uint32_t r[64];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
-          tmem_ld_wait();
-          if (valid < 64) {
-#pragma unroll
-            for (int e = 0; e < 64; ++e)
-              if (e >= valid) r[e] = 0xff800000u;  // -inf
-          }
-          float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
-#pragma unroll
-          for (int e = 0; e < 64; e += 4) {
-            c0 = fmaxf(c0, __uint_as_float(r[e + 0]));
-            c1 = fmaxf(c1, __uint_as_float(r[e + 1]));
-            c2 = fmaxf(c2, __uint_as_float(r[e + 2]));
-            c3 = fmaxf(c3, __uint_as_float(r[e + 3]));
-          }
-          const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-          if (exact) {
-            const float m_new = fmaxf(m_run, cm);
-            if (m_new > -INFINITY) {
-              const float mb = m_new * sc2;
-              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-              for (int e = 0; e < 64; e += 4) {
-                a0 += ex2(fmaf(__uint_as_float(r[e + 0]), sc2, -mb));
-                a1 += ex2(fmaf(__uint_as_float(r[e + 1]), sc2, -mb));
-                a2 += ex2(fmaf(__uint_as_float(r[e + 2]), sc2, -mb));
-                a3 += ex2(fmaf(__uint_as_float(r[e + 3]), sc2, -mb));
-              }
-              l_run = l_run * ex2((m_run - m_new) * sc2) + ((a0 + a1) + (a2 + a3));
-            }
-            m_run = m_new;
-          } else {
-            m_run = fmaxf(m_run, cm);
-          }
-        }
+        const int valid = atom_info(p, atoms_per_slot, A).valid;
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[buf]);
+        if (lane == 0) mbar_arrive(&s_empty[sb]);  // scores are in registers: the MMA warp may overwrite this S tile
+        if (valid < 64) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (e >= valid) r[e] = 0xff800000u;  // -inf
+        }
+        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+          c0 = fmaxf(c0, __uint_as_float(r[e + 0]));
+          c1 = fmaxf(c1, __uint_as_float(r[e + 1]));
+          c2 = fmaxf(c2, __uint_as_float(r[e + 2]));
+          c3 = fmaxf(c3, __uint_as_float(r[e + 3]));
+        }
+        const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+        if (exact) {
+          const float m_new = fmaxf(m_run, cm);
+          if (m_new > -INFINITY) {
+            const float mb = m_new * sc2;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+              a0 += ex2(fmaf(__uint_as_float(r[e + 0]), sc2, -mb));
+              a1 += ex2(fmaf(__uint_as_float(r[e + 1]), sc2, -mb));
+              a2 += ex2(fmaf(__uint_as_float(r[e + 2]), sc2, -mb));
+              a3 += ex2(fmaf(__uint_as_float(r[e + 3]), sc2, -mb));
+            }
+            l_run = l_run * ex2((m_run - m_new) * sc2) + ((a0 + a1) + (a2 + a3));
+          }
+          m_run = m_new;
+        } else {
+          m_run = fmaxf(m_run, cm);
+        }
       }
-      // merge the two warpgroups' running (max, sum)
+      // merge the two warpgroups' running (max, sum); also orders every pass-1 barrier phase before pass 2
       xchg[(wg * 128 + row) * 2 + 0] = m_run;
       xchg[(wg * 128 + row) * 2 + 1] = l_run;
       named_bar_sync(3, 256);
@@ -350,133 +338,125 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       const float* xe = p.xedit;
       const bool row_ops = row_mode == FZ_ATTN_CROSSEDIT || (p.acc && edited);
       // ------------------------------ pass 2: probabilities -> P tile (-> cache) ------------------------------
-      for (int b = 0; b < n_blocks; ++b, ++g) {
-        if ((b & 1) != wg) continue;
-        const int buf = g & 1, pb = b & 1;
-        mbar_wait(&s_full[buf], (g >> 1) & 1);
+      for (int A = wg; A < n_atoms; A += 2) {
+        const int g = n_atoms + A, sb = g & 3, pb = A & 3;
+        const AtomInfo ai = atom_info(p, atoms_per_slot, A);
+        mbar_wait(&s_full[sb], (g >> 2) & 1);
         tc_fence_after();
-        if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<0>();  // this warpgroup's P buffer was read by its previous store
-        mbar_wait(&p_empty[pb], ((b >> 1) & 1) ^ 1);
-        named_bar_sync(1 + wg, 128);
-        if (blend) { mbar_wait(base_full, b & 1); }
-        uint8_t* pbuf = s_p + pb * 2 * kAtomBytes;
-        const int na = min(2, n_atoms - 2 * b);
-        for (int a = 0; a < na; ++a) {
-          const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
-          uint8_t* prow = pbuf + a * kAtomBytes + row * 128;
-          uint32_t r[64];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + buf * 128 + a * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
-          tmem_ld_wait();
-          if (ai.valid < 64) {
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        if (ai.valid < 64) {
 #pragma unroll
-            for (int e = 0; e < 64; ++e)
-              if (e >= ai.valid) r[e] = 0xff800000u;
-          }
-          float* pv = reinterpret_cast<float*>(r);
-          if (exact) {
+          for (int e = 0; e < 64; ++e)
+            if (e >= ai.valid) r[e] = 0xff800000u;
+        }
+        float* pv = reinterpret_cast<float*>(r);
+        if (exact) {
 #pragma unroll
-            for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2)) * inv_l;
-          } else {
+          for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2)) * inv_l;
+        } else {
 #pragma unroll
-            for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+          for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
-          }
-          if (row_ops) {
+          for (int e = 0; e < 64; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
+        }
+        if (row_ops) {
 #pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-              float* pc = pv + c;
-              // key index n = ai.k0 + c + e (single slot).  cur = fp16(p); optional running sum; optional edit (in fp32, one rounding)
-              const int n0 = ai.k0 + c;
-              const long long rbase = ((static_cast<long long>(fc) * p.heads + head) * p.S_q + min(q, p.S_q - 1));
-              if (p.acc && row_ok) {
-                __half* ap = p.acc + rbase * p.acc_ld + n0;
+          for (int c = 0; c < 64; c += 32) {
+            float* pc = pv + c;
+            // key index n = ai.k0 + c + e (single slot).  cur = fp16(p); optional running sum; optional edit (in fp32, one rounding)
+            const int n0 = ai.k0 + c;
+            const long long rbase = ((static_cast<long long>(fc) * p.heads + head) * p.S_q + min(q, p.S_q - 1));
+            if (p.acc && row_ok) {
+              __half* ap = p.acc + rbase * p.acc_ld + n0;
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                  if (n0 + e < p.acc_ld) {
-                    uint4 v = *reinterpret_cast<uint4*>(ap + e);
-                    __half* hv = reinterpret_cast<__half*>(&v);
+              for (int e = 0; e < 32; e += 8) {
+                if (n0 + e < p.acc_ld) {
+                  uint4 v = *reinterpret_cast<uint4*>(ap + e);
+                  __half* hv = reinterpret_cast<__half*>(&v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(__half2float(hv[j]) + __half2float(__float2half_rn(pc[e + j])));
-                    *reinterpret_cast<uint4*>(ap + e) = v;
-                  }
-                }
-              }
-              if (row_mode == FZ_ATTN_CROSSEDIT) {
-                const __half* brow = p.base_rows + rbase * p.base_ld;
-                const int xmode = static_cast<int>(xe[0]);  // 0 refine, 1 replace
-                const float* x_alpha = xe + 8;              // [80] cross_replace_alpha of this step
-                const float* x_eq = xe + 8 + 80;            // [80] equalizer (1 when absent)
-                const float* x_a = xe + 8 + 160;            // [80] refine alphas
-                const float* x_map = xe + 8 + 240;          // [80] refine mapper (as float)
-                const float* x_M = xe + 8 + 320;            // [80][80] replace matrix M[w][n]
-                float rr[32];
-                if (xmode == 1) {
-#pragma unroll
-                  for (int e = 0; e < 32; ++e) rr[e] = 0.f;
-                  for (int w = 0; w < p.keys_per_slot; ++w) {
-                    const float bw = __half2float(brow[w]);
-                    const float* mrow_p = x_M + w * 80 + n0;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                      if (n0 + e < 80) rr[e] += bw * __ldg(mrow_p + e);
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  const int n = n0 + e;
-                  if (n < p.keys_per_slot) {
-                    const float cur = __half2float(__float2half_rn(pc[e]));
-                    float R;
-                    if (xmode == 1) R = rr[e];
-                    else {
-                      int mi = static_cast<int>(__ldg(x_map + n));
-                      if (mi < 0) mi += p.keys_per_slot;  // python negative index (masked by a[n] == 0)
-                      const float an = __ldg(x_a + n);
-                      R = __half2float(brow[mi]) * an + cur * (1.f - an);
-                    }
-                    R *= __ldg(x_eq + n);
-                    const float al = __ldg(x_alpha + n);
-                    pc[e] = R * al + (1.f - al) * cur;
-                  }
+                  for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(__half2float(hv[j]) + __half2float(__float2half_rn(pc[e + j])));
+                  *reinterpret_cast<uint4*>(ap + e) = v;
                 }
               }
             }
-          }
-          // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
+            if (row_mode == FZ_ATTN_CROSSEDIT) {
+              const __half* brow = p.base_rows + rbase * p.base_ld;
+              const int xmode = static_cast<int>(xe[0]);  // 0 refine, 1 replace
+              const float* x_alpha = xe + 8;              // [80] cross_replace_alpha of this step
+              const float* x_eq = xe + 8 + 80;            // [80] equalizer (1 when absent)
+              const float* x_a = xe + 8 + 160;            // [80] refine alphas
+              const float* x_map = xe + 8 + 240;          // [80] refine mapper (as float)
+              const float* x_M = xe + 8 + 320;            // [80][80] replace matrix M[w][n]
+              float rr[32];
+              if (xmode == 1) {
 #pragma unroll
-          for (int e = 0; e < 64; e += 8) {
-            uint4 v;
-            v.x = pack_half2(pv[e + 0], pv[e + 1]);
-            v.y = pack_half2(pv[e + 2], pv[e + 3]);
-            v.z = pack_half2(pv[e + 4], pv[e + 5]);
-            v.w = pack_half2(pv[e + 6], pv[e + 7]);
-            const int j = e >> 3;
-            *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
-          }
-          if (blend) {
-            if (mrow == 0.f) {
-              const uint8_t* srow = s_pbase + a * kAtomBytes + row * 128;
+                for (int e = 0; e < 32; ++e) rr[e] = 0.f;
+                for (int w = 0; w < p.keys_per_slot; ++w) {
+                  const float bw = __half2float(brow[w]);
+                  const float* mrow_p = x_M + w * 80 + n0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(prow + j * 16) = *reinterpret_cast<const uint4*>(srow + j * 16);
+                  for (int e = 0; e < 32; ++e)
+                    if (n0 + e < 80) rr[e] += bw * __ldg(mrow_p + e);
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int n = n0 + e;
+                if (n < p.keys_per_slot) {
+                  const float cur = __half2float(__float2half_rn(pc[e]));
+                  float R;
+                  if (xmode == 1) R = rr[e];
+                  else {
+                    int mi = static_cast<int>(__ldg(x_map + n));
+                    if (mi < 0) mi += p.keys_per_slot;  // python negative index (masked by a[n] == 0)
+                    const float an = __ldg(x_a + n);
+                    R = __half2float(brow[mi]) * an + cur * (1.f - an);
+                  }
+                  R *= __ldg(x_eq + n);
+                  const float al = __ldg(x_alpha + n);
+                  pc[e] = R * al + (1.f - al) * cur;
+                }
+              }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[buf]);
-          if (blend) mbar_arrive(base_empty);
+        // the P buffer must be free: its previous PV MMA done (p_empty) and, for STORE, its previous TMA store done reading
+        if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<1>();
+        mbar_wait(&p_empty[pb], ((A >> 2) & 1) ^ 1);
+        named_bar_sync(1 + wg, 128);
+        uint8_t* prow = s_p + pb * kAtomBytes + row * 128;
+        // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
+#pragma unroll
+        for (int e = 0; e < 64; e += 8) {
+          uint4 v;
+          v.x = pack_half2(pv[e + 0], pv[e + 1]);
+          v.y = pack_half2(pv[e + 2], pv[e + 3]);
+          v.z = pack_half2(pv[e + 4], pv[e + 5]);
+          v.w = pack_half2(pv[e + 6], pv[e + 7]);
+          const int j = e >> 3;
+          *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
+        }
+        if (blend) {
+          mbar_wait(&base_full[wg], (A >> 1) & 1);
+          if (mrow == 0.f) {
+            const uint8_t* srow = s_pbase + wg * kAtomBytes + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(prow + j * 16) = *reinterpret_cast<const uint4*>(srow + j * 16);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&base_empty[wg]);
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + wg, 128);
         if (st == 0) {
           if (row_mode == FZ_ATTN_STORE) {
-            for (int a = 0; a < na; ++a) {
-              const AtomInfo ai = atom_info(p, atoms_per_slot, 2 * b + a);
-              tma_store_5d(&p.tmStore, pbuf + a * kAtomBytes, ai.k0, ai.slot, q0, head, fc);
-            }
+            tma_store_5d(&p.tmStore, s_p + pb * kAtomBytes, ai.k0, ai.slot, q0, head, fc);
             tma_store_commit();
           }
           mbar_arrive(&p_full[pb]);
@@ -489,7 +469,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
         l_run += xchg[((wg ^ 1) * 128 + row) * 2];
       }
     }
-    // ------------------------------ epilogue: O (TMEM) -> fp16 -> global ------------------------------
+    // ------------------------------ epilogue: O (TMEM) -> fp16 -> global (16-column chunks alternate between the warpgroups) ------------------------------
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float o_scale = (!replace && !exact) ? (1.0f / l_run) : 1.0f;
@@ -591,10 +571,10 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     p.tmBase = p.tmQ;
   }
   // shared memory plan
-  const int stage_bytes = std::max(kAtomBytes, (p.d_pad * 128 + 1023) / 1024 * 1024);
+  const int stage_bytes = std::max(8192, (p.d_pad * 128 + 1023) / 1024 * 1024);
   const int fixed = p.nd * kAtomBytes + 4 * kAtomBytes + (a->row_mode == FZ_ATTN_BLEND ? 2 * kAtomBytes : 0) + 1024 + 3072;
-  int stages = 6;
-  while (stages > 2 && fixed + stages * stage_bytes > 225 * 1024) --stages;
+  int stages = 10;
+  while (stages > 3 && fixed + stages * stage_bytes > 225 * 1024) --stages;
   FZ_CHECK_ARG(fixed + stages * stage_bytes <= 227 * 1024, "fz_attention: shared memory plan does not fit (d=%d)", a->d);
   p.ring_stages = stages; p.ring_stage_bytes = stage_bytes;
   const int smem = fixed + stages * stage_bytes;

@@ -69,15 +69,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must become a trap (the launch fails with an error), never a hung GPU box.
-#ifndef FZ_MBAR_SPIN_LIMIT
-#define FZ_MBAR_SPIN_LIMIT (1u << 26)
+// Bounded wait: a protocol bug must become a trap (the launch fails with an error) within ~2 s of wall time, never a hung GPU box.
+#ifndef FZ_MBAR_TIMEOUT_NS
+#define FZ_MBAR_TIMEOUT_NS 2000000000ull
 #endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > FZ_MBAR_SPIN_LIMIT) {
-      printf("fz: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
+    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > FZ_MBAR_TIMEOUT_NS) {
+      printf("fz: mbarrier wait timed out (block %d,%d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
+             (void*)bar, parity);
       __trap();
     }
   }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
   const int p1 = min(HW, p0 + px_per_cta);
   if (ty < TY) {
     const __half* xb = x + (static_cast<long long>(nb) * HW) * C;
-#pragma unroll 2
+#pragma unroll 4
     for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
       for (int s = 0; s < kGnMaxSlots; ++s) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
   const int p0 = blockIdx.x * px_per_cta;
   const int p1 = min(HW, p0 + px_per_cta);
   const long long base = (static_cast<long long>(nb) * HW) * C;
-#pragma unroll 2
+#pragma unroll 4
   for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
     for (int s = 0; s < kGnMaxSlots; ++s) {

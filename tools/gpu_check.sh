@@ -10,7 +10,7 @@ rc_all=0
 for f in $files; do
   name=$(basename $f .py)
   echo "=== $f" | tee -a gpurun_out/gpu_check.log
-  timeout 900 python -m pytest $f -m gpu -q -x --timeout 600 -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  timeout 600 python -m pytest $f -m gpu -q -x --timeout 300 -p no:cacheprovider > gpurun_out/$name.log 2>&1
   rc=$?
   tail -n 25 gpurun_out/$name.log | tee -a gpurun_out/gpu_check.log
   echo "rc=$rc" | tee -a gpurun_out/gpu_check.log
