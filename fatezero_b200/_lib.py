@@ -31,7 +31,7 @@ class AttnArgs(C.Structure):
         ("d", c_int), ("heads", c_int), ("F", c_int), ("BF", c_int),
         ("scale", c_float), ("src_index", C.POINTER(c_int)), ("edit_bf_start", c_int), ("row_mode", c_int),
         ("store", c_void_p), ("base", c_void_p), ("cache_ld", c_ll), ("acc", c_void_p), ("acc_ld", c_ll),
-        ("xedit", c_void_p), ("mask", c_void_p),
+        ("xedit", c_void_p), ("mask", c_void_p), ("dbg", c_void_p),
     ]
 
 

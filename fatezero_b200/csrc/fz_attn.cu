@@ -56,6 +56,7 @@ struct AttnParams {
   const float* mask;    // BLEND: [Fc, S_q] 1 = keep current row, 0 = take cached row
   __half* out;          // [BF*S_q, ldo], this head's columns start at head*d
   long long ldo;
+  long long* dbg;       // optional [32] cycle counters written by CTA (0,0,0) (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -68,6 +69,25 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Optional in-kernel cycle accounting (compile with -DFZ_ATTN_PROFILE): adds clock reads around the waits of CTA (0,0,0).
+#ifdef FZ_ATTN_PROFILE
+#define FZ_TIMED(slot, stmt)                       \
+  do {                                             \
+    if (dbg_on) {                                  \
+      const long long _t0 = clock64();             \
+      stmt;                                        \
+      dbg_acc[slot] += clock64() - _t0;            \
+    } else {                                       \
+      stmt;                                        \
+    }                                              \
+  } while (0)
+#else
+#define FZ_TIMED(slot, stmt) \
+  do {                       \
+    stmt;                    \
+  } while (0)
+#endif
 
 struct AtomInfo {
   int slot, k0, valid;
@@ -146,27 +166,41 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+#ifdef FZ_ATTN_PROFILE
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;  // warp-uniform
+#else
+  constexpr bool dbg_on = false;
+#endif
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
 
-  if (warp == 0) {
+  // Warp roles: 0..7 softmax (two warpgroups), 8 = TMA producer, 9 = MMA issuer.  The issue arbiter favours higher warp ids, and the
+  // MMA warp gates everything downstream, so it gets the highest id (as warp 1 it was starved by the softmax warps of its scheduler).
+  if (warp == 8) {
     // =========================================== TMA producer ===========================================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
-      auto load_k = [&](int A) {
-        const AtomInfo ai = atom_info(p, atoms_per_slot, A);
-        const int src = p.src_index[ai.slot][bf];
+      // K chunks of an atom PAIR are interleaved (A.c0, A+1.c0, A.c1, ...) to match the MMA warp's interleaved issue order
+      auto load_k_pair = [&](int A0) {
+        const int n = min(2, n_atoms - A0);
+        const AtomInfo a0 = atom_info(p, atoms_per_slot, A0);
+        const AtomInfo a1 = atom_info(p, atoms_per_slot, min(A0 + 1, n_atoms - 1));
         for (int c = 0; c < p.nd; ++c) {
-          mbar_wait(&ring_empty[stage], phase ^ 1);
-          mbar_expect_tx(&ring_full[stage], 64 * 128);
-          tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmK, &ring_full[stage], c * 64, head, ai.k0, src);
-          advance();
+          for (int j = 0; j < n; ++j) {
+            const AtomInfo& ai = j ? a1 : a0;
+            mbar_wait(&ring_empty[stage], phase ^ 1);
+            mbar_expect_tx(&ring_full[stage], 64 * 128);
+            tma_load_4d(s_ring + stage * p.ring_stage_bytes, &p.tmK, &ring_full[stage], c * 64, head, ai.k0, p.src_index[ai.slot][bf]);
+            advance();
+          }
         }
       };
       auto load_v = [&](int A) {
@@ -184,83 +218,165 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       if (!replace) {
         mbar_expect_tx(q_full, p.nd * kAtomBytes);
         for (int c = 0; c < p.nd; ++c) tma_load_4d(s_q + c * kAtomBytes, &p.tmQ, q_full, c * 64, head, q0, bf);
-        for (int A = 0; A < n_atoms; ++A) load_k(A);  // pass 1
-        load_k(0);                                     // pass 2 (two S tiles of look-ahead, one per warpgroup)
-        if (n_atoms > 1) load_k(1);
-        for (int A = 0; A < n_atoms; ++A) {
-          if (A + 2 < n_atoms) load_k(A + 2);
+        for (int A = 0; A < n_atoms; A += 2) load_k_pair(A);  // pass 1
+        load_k_pair(0);                                        // pass 2: one pair of S tiles of look-ahead
+        for (int A = 0; A < n_atoms; A += 2) {
+          if (A + 2 < n_atoms) load_k_pair(A + 2);
+          const int n = min(2, n_atoms - A);
           if (blend) {
-            const int w = A & 1;
-            mbar_wait(&base_empty[w], ((A >> 1) & 1) ^ 1);
-            load_base(A, s_pbase + w * kAtomBytes, &base_full[w]);
+            for (int j = 0; j < n; ++j) {
+              const int w = (A + j) & 1;
+              mbar_wait(&base_empty[w], (((A + j) >> 1) & 1) ^ 1);
+              load_base(A + j, s_pbase + w * kAtomBytes, &base_full[w]);
+            }
           }
-          load_v(A);
+          for (int j = 0; j < n; ++j) load_v(A + j);
         }
       } else {
-        for (int A = 0; A < n_atoms; ++A) {
-          const int pb = A & 3;
-          mbar_wait(&p_empty[pb], ((A >> 2) & 1) ^ 1);
-          load_base(A, s_p + pb * kAtomBytes, &p_full[pb]);
-          load_v(A);
+        for (int A = 0; A < n_atoms; A += 2) {
+          const int n = min(2, n_atoms - A);
+          for (int j = 0; j < n; ++j) {
+            const int pb = (A + j) & 3;
+            mbar_wait(&p_empty[pb], (((A + j) >> 2) & 1) ^ 1);
+            load_base(A + j, s_p + pb * kAtomBytes, &p_full[pb]);
+          }
+          for (int j = 0; j < n; ++j) load_v(A + j);
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // =========================================== MMA issuer ===========================================
-    if (elect_one()) {
+    // The whole warp runs the control flow convergently (addresses / descriptors stay in the uniform datapath); only the
+    // tcgen05.mma / tcgen05.commit instructions themselves are issued by the elected lane.
+    const bool leader = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++stage == p.ring_stages) { stage = 0; phase ^= 1; } };
+      // The issuing thread is on the critical path of every 64-key atom (each UMMA here is only 24-32 tensor cycles), so its
+      // instruction stream is kept minimal: descriptor high words are constants, low words advance by adds, loops are unrolled.
       const uint32_t idesc_o = umma_idesc_f16(128, p.d_pad);
       const uint32_t idesc_s = umma_idesc_f16(128, 64);
-      int g = 0;  // S-tile counter across both passes
-      auto issue_s = [&]() {
-        const int sb = g & 3;
-        mbar_wait(&s_empty[sb], ((g >> 2) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + sb * 64;
-        for (int c = 0; c < p.nd; ++c) {
-          mbar_wait(&ring_full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(s_q + c * kAtomBytes);
-          const uint32_t sb_addr = smem_u32(s_ring + stage * p.ring_stage_bytes);
-          const int ksteps = min(4, (p.d - c * 64 + 15) / 16);
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb_addr + k * 32), idesc_s, (c | k) ? 1u : 0u);
-          umma_commit(&ring_empty[stage]);
-          advance();
-        }
-        umma_commit(&s_full[sb]);
-        ++g;
+      const uint64_t desc_hi = umma_desc_k_sw128(0);                       // everything except the 14-bit start address
+      const uint32_t ring_lo0 = (smem_u32(s_ring) & 0x3FFFF) >> 4;
+      const uint32_t stage_lo = static_cast<uint32_t>(p.ring_stage_bytes) >> 4;
+      const uint32_t q_lo = (smem_u32(s_q) & 0x3FFFF) >> 4;
+      const uint32_t p_lo0 = (smem_u32(s_p) & 0x3FFFF) >> 4;
+      uint32_t ring_lo = ring_lo0;                                         // descriptor low word of the current ring stage
+      auto advance2 = [&]() {
+        ring_lo += stage_lo;
+        if (++stage == p.ring_stages) { stage = 0; phase ^= 1; ring_lo = ring_lo0; }
       };
-      auto issue_pv = [&](int A) {
-        const int pb = A & 3;
-        mbar_wait(&p_full[pb], (A >> 2) & 1);
+      const int ks_last = min(4, (p.d - (p.nd - 1) * 64 + 15) / 16);     // k-steps of the last 64-wide head-dim chunk
+      // Consecutive tcgen05.mma into the SAME accumulator serialise on the tensor pipe's accumulate latency (measured ~180 cycles per
+      // dependent M128xN64 / N48 instruction), so atoms are issued in PAIRS with their k-steps interleaved: S(A), S(A+1) target two S
+      // buffers and PV(A), PV(A+1) two O accumulators (O0 even atoms, O1 odd atoms, summed in the epilogue) -> 2 independent chains.
+      const bool dual = p.d_pad <= 128 && n_atoms >= 2;
+      const uint32_t tmem_o1 = dual ? tmem_o + 128 : tmem_o;
+      int g = 0;  // S-tile counter across both passes
+      auto issue_s_pair = [&](int A0) {
+        const int n = min(2, n_atoms - A0);
+        const int sb0 = g & 3, sb1 = (g + 1) & 3;
+        FZ_TIMED(0, mbar_wait(&s_empty[sb0], ((g >> 2) & 1) ^ 1));
+        if (n == 2) FZ_TIMED(0, mbar_wait(&s_empty[sb1], (((g + 1) >> 2) & 1) ^ 1));
         tc_fence_after();
-        mbar_wait(&ring_full[stage], phase);
+        const uint32_t d0 = tmem_base + sb0 * 64, d1 = tmem_base + sb1 * 64;
+        uint32_t a_lo = q_lo;
+        for (int c = 0; c < p.nd; ++c) {
+          FZ_TIMED(1, mbar_wait(&ring_full[stage], phase));
+          const uint32_t lo0 = ring_lo;
+          uint64_t* e0 = &ring_empty[stage];
+          advance2();
+          uint32_t lo1 = lo0;
+          uint64_t* e1 = e0;
+          if (n == 2) {
+            FZ_TIMED(1, mbar_wait(&ring_full[stage], phase));
+            lo1 = ring_lo;
+            e1 = &ring_empty[stage];
+            advance2();
+          }
+          tc_fence_after();
+          const int ksteps = (c == p.nd - 1) ? ks_last : 4;
+          const long long _tm0 = dbg_on ? clock64() : 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (leader && k < ksteps) {
+              umma_f16_ss(d0, desc_hi | (a_lo + 2 * k), desc_hi | (lo0 + 2 * k), idesc_s, (c | k) ? 1u : 0u);
+              if (n == 2) umma_f16_ss(d1, desc_hi | (a_lo + 2 * k), desc_hi | (lo1 + 2 * k), idesc_s, (c | k) ? 1u : 0u);
+            }
+          }
+          const long long _tm1 = dbg_on ? clock64() : 0;
+          if (leader) {
+            umma_commit(e0);
+            if (n == 2) umma_commit(e1);
+          }
+          if (dbg_on) { dbg_acc[5] += _tm1 - _tm0; dbg_acc[6] += clock64() - _tm1; }
+          a_lo += kAtomBytes >> 4;
+        }
+        if (leader) {
+          umma_commit(&s_full[sb0]);
+          if (n == 2) umma_commit(&s_full[sb1]);
+        }
+        __syncwarp();
+        g += n;
+      };
+      auto issue_pv_pair = [&](int A0) {
+        const int n = min(2, n_atoms - A0);
+        const int pb0 = A0 & 3, pb1 = (A0 + 1) & 3;
+        FZ_TIMED(2, mbar_wait(&p_full[pb0], (A0 >> 2) & 1));
+        if (n == 2) FZ_TIMED(2, mbar_wait(&p_full[pb1], ((A0 + 1) >> 2) & 1));
+        FZ_TIMED(3, mbar_wait(&ring_full[stage], phase));
+        const uint32_t v0 = ring_lo;
+        uint64_t* e0 = &ring_empty[stage];
+        advance2();
+        uint32_t v1 = v0;
+        uint64_t* e1 = e0;
+        if (n == 2) {
+          FZ_TIMED(3, mbar_wait(&ring_full[stage], phase));
+          v1 = ring_lo;
+          e1 = &ring_empty[stage];
+          advance2();
+        }
         tc_fence_after();
-        const uint32_t sa = smem_u32(s_p + pb * kAtomBytes);
-        const uint32_t sb_addr = smem_u32(s_ring + stage * p.ring_stage_bytes);
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(tmem_o, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb_addr + k * 32), idesc_o, (A | k) ? 1u : 0u);
-        umma_commit(&ring_empty[stage]);
-        advance();
-        umma_commit(&p_empty[pb]);
+        const uint32_t a0 = p_lo0 + pb0 * (kAtomBytes >> 4), a1 = p_lo0 + pb1 * (kAtomBytes >> 4);
+        const long long _tp0 = dbg_on ? clock64() : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (leader) {
+            umma_f16_ss(tmem_o, desc_hi | (a0 + 2 * k), desc_hi | (v0 + 2 * k), idesc_o, (A0 | k) ? 1u : 0u);
+            if (n == 2) umma_f16_ss(tmem_o1, desc_hi | (a1 + 2 * k), desc_hi | (v1 + 2 * k), idesc_o, (dual ? (A0 | k) : 1) ? 1u : 0u);
+          }
+        }
+        if (dbg_on) dbg_acc[7] += clock64() - _tp0;
+        if (leader) {
+          umma_commit(e0);
+          umma_commit(&p_empty[pb0]);
+          if (n == 2) {
+            umma_commit(e1);
+            umma_commit(&p_empty[pb1]);
+          }
+        }
+        __syncwarp();
       };
       if (!replace) {
         mbar_wait(q_full, 0);
         tc_fence_after();
-        for (int A = 0; A < n_atoms; ++A) issue_s();
-        issue_s();
-        if (n_atoms > 1) issue_s();
-        for (int A = 0; A < n_atoms; ++A) {
-          if (A + 2 < n_atoms) issue_s();
-          issue_pv(A);
+        for (int A = 0; A < n_atoms; A += 2) issue_s_pair(A);
+        issue_s_pair(0);
+        for (int A = 0; A < n_atoms; A += 2) {
+          if (A + 2 < n_atoms) issue_s_pair(A + 2);
+          issue_pv_pair(A);
         }
       } else {
-        for (int A = 0; A < n_atoms; ++A) issue_pv(A);
+        for (int A = 0; A < n_atoms; A += 2) issue_pv_pair(A);
       }
-      umma_commit(o_full);
+      if (leader) umma_commit(o_full);
+      if (dbg_on && leader) {
+        for (int i = 0; i < 4; ++i) p.dbg[i] = dbg_acc[i];
+        p.dbg[4] = clock64() - dbg_t0;
+        p.dbg[25] = dbg_acc[5]; p.dbg[26] = dbg_acc[6]; p.dbg[27] = dbg_acc[7];
+
+      }
     }
   } else {
     // =========================================== softmax / epilogue warpgroups ===========================================
@@ -269,15 +385,15 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
     const int q = q0 + row;
     const bool row_ok = q < p.S_q;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const int wg = (warp - 2) >> 2;            // handles atoms with (A & 1) == wg
-    const int st = (threadIdx.x - 64) & 127;   // 0..127 within the warpgroup
+    const int wg = warp >> 2;                  // handles atoms with (A & 1) == wg
+    const int st = threadIdx.x & 127;          // 0..127 within the warpgroup
     float m_run = -INFINITY, l_run = 0.f;
     if (!replace) {
       // ------------------------------ pass 1: row max of the raw scores (and sum of exponentials when exact) ------------------------------
       const float sc2 = p.scale_log2;
       for (int A = wg; A < n_atoms; A += 2) {
         const int g = A, sb = g & 3;
-        mbar_wait(&s_full[sb], (g >> 2) & 1);
+        FZ_TIMED(0, mbar_wait(&s_full[sb], (g >> 2) & 1));
         tc_fence_after();
         const int valid = atom_info(p, atoms_per_slot, A).valid;
         uint32_t r[64];
@@ -331,6 +447,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
         m_run = m_new;
       }
       named_bar_sync(3, 256);
+      const long long dbg_p1 = clock64() - dbg_t0;
       const float inv_l = exact ? (1.0f / l_run) : 1.0f;
       const float mb2 = m_run * sc2;
       float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lf3 = 0.f;
@@ -341,7 +458,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       for (int A = wg; A < n_atoms; A += 2) {
         const int g = n_atoms + A, sb = g & 3, pb = A & 3;
         const AtomInfo ai = atom_info(p, atoms_per_slot, A);
-        mbar_wait(&s_full[sb], (g >> 2) & 1);
+        FZ_TIMED(1, mbar_wait(&s_full[sb], (g >> 2) & 1));
         tc_fence_after();
         uint32_t r[64];
         tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
@@ -428,8 +545,8 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
         }
         // the P buffer must be free: its previous PV MMA done (p_empty) and, for STORE, its previous TMA store done reading
         if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_read<1>();
-        mbar_wait(&p_empty[pb], ((A >> 2) & 1) ^ 1);
-        named_bar_sync(1 + wg, 128);
+        FZ_TIMED(2, mbar_wait(&p_empty[pb], ((A >> 2) & 1) ^ 1));
+        FZ_TIMED(3, named_bar_sync(1 + wg, 128));
         uint8_t* prow = s_p + pb * kAtomBytes + row * 128;
         // swizzled 16-byte stores: chunk j of row `row` lands at chunk (j ^ (row & 7))
 #pragma unroll
@@ -453,7 +570,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
           if (lane == 0) mbar_arrive(&base_empty[wg]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1 + wg, 128);
+        FZ_TIMED(4, named_bar_sync(1 + wg, 128));
         if (st == 0) {
           if (row_mode == FZ_ATTN_STORE) {
             tma_store_5d(&p.tmStore, s_p + pb * kAtomBytes, ai.k0, ai.slot, q0, head, fc);
@@ -462,6 +579,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
           mbar_arrive(&p_full[pb]);
         }
       }
+      if (dbg_on && warp == 0 && lane == 0) p.dbg[24] = dbg_p1;
       if (!exact) {
         l_run = (lf0 + lf1) + (lf2 + lf3);
         xchg[(wg * 128 + row) * 2] = l_run;
@@ -470,14 +588,23 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       }
     }
     // ------------------------------ epilogue: O (TMEM) -> fp16 -> global (16-column chunks alternate between the warpgroups) ------------------------------
-    mbar_wait(o_full, 0);
+    if (dbg_on && (warp == 0 || warp == 4)) dbg_acc[6] = clock64() - dbg_t0;  // end of pass 2
+    FZ_TIMED(5, mbar_wait(o_full, 0));
     tc_fence_after();
     const float o_scale = (!replace && !exact) ? (1.0f / l_run) : 1.0f;
     __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + min(q, p.S_q - 1)) * p.ldo + head * p.d;
 #pragma unroll 1
+    const bool dual_o = p.d_pad <= 128 && n_atoms >= 2;  // odd atoms accumulated into a second O tile at +128 columns
     for (int c = wg * 16; c < p.d_pad; c += 32) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_o + lane_addr + c, r);
+      if (dual_o) {
+        uint32_t r1[16];
+        tmem_ld_32x32b_x16(tmem_o + 128 + lane_addr + c, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r1[e]));
+      }
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -494,10 +621,15 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
       }
     }
     if (row_mode == FZ_ATTN_STORE && st == 0) tma_store_wait_all<0>();
+    if (dbg_on && lane == 0 && (warp == 0 || warp == 4)) {
+      const int base = warp == 0 ? 8 : 16;
+      for (int i = 0; i < 7; ++i) p.dbg[base + i] = dbg_acc[i];
+      p.dbg[base + 7] = clock64() - dbg_t0;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -534,6 +666,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
   p.base_rows = static_cast<const __half*>(a->base); p.base_ld = a->cache_ld;
   p.xedit = a->xedit; p.mask = a->mask;
   p.out = static_cast<__half*>(a->out); p.ldo = a->ldo;
+  p.dbg = static_cast<long long*>(a->dbg);
   const int Fc = a->BF - a->edit_bf_start;
   if (a->row_mode == FZ_ATTN_STORE) FZ_CHECK_ARG(a->store, "fz_attention: STORE needs a cache slab");
   if (a->row_mode == FZ_ATTN_REPLACE || a->row_mode == FZ_ATTN_BLEND || a->row_mode == FZ_ATTN_CROSSEDIT)

@@ -78,17 +78,27 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path kept out of line: the inlined fast path is one try_wait + branch (the MMA-issuing warps execute thousands of waits)
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > FZ_MBAR_TIMEOUT_NS) {
-      printf("fz: mbarrier wait timed out (block %d,%d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
-             (void*)bar, parity);
+      printf("fz: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
+             bar_addr, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA store / tcgen05.mma operand reads)

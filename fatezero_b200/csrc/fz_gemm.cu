@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N);
+      const uint64_t desc_hi = umma_desc_k_sw128(0);  // constant descriptor fields; only the 14-bit start address varies
+      const uint32_t smem_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -157,11 +159,11 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t a_lo = smem_lo0 + stage * (Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (kATileBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+            umma_f16_ss(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it | k) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }

@@ -234,7 +234,7 @@ def blend_mask(maps: Sequence[torch.Tensor], word_w: torch.Tensor, th: float, h:
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, S_q: int, keys_per_slot: int, n_src: int, d: int,
               heads: int, F: int, BF: int, scale: float, src_index: Sequence[Sequence[int]], edit_bf_start: int = 0,
-              row_mode: int = _lib.ATTN_NONE, store=None, base=None, cache_ld: int = 0, acc=None, xedit=None, mask=None):
+              row_mode: int = _lib.ATTN_NONE, store=None, base=None, cache_ld: int = 0, acc=None, xedit=None, mask=None, dbg=None):
     """q/k: strided 2-D views (rows, ld) whose column h*d starts head h; vt [n_src, heads, d, vt_ld]; out [BF*S_q, ldo]."""
     a = AttnArgs()
     a.q, a.ldq = _p(q), q.stride(0)
@@ -251,5 +251,6 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     a.store, a.base, a.cache_ld = _p(store), _p(base), cache_ld
     a.acc, a.acc_ld = _p(acc), (acc.stride(2) if acc is not None else 0)
     a.xedit, a.mask = _p(xedit), _p(mask)
+    a.dbg = _p(dbg)
     _lib.call("fz_attention_f16", C.byref(a), _stream())
     return out

@@ -95,6 +95,7 @@ typedef struct fz_attn_args {
   void* acc;       long long acc_ld;/* fp16 running sum slab or NULL (attention_store.py:95-101)                    */
   const float* xedit;               /* device table, see above                                                       */
   const float* mask;                /* device [BF-edit_bf_start, S_q], 1 = keep current row                          */
+  void* dbg;                        /* optional device int64[32]: cycle counters of CTA (0,0,0) (profiling aid) or NULL */
 } fz_attn_args_t;
 
 int fz_attention_f16(const fz_attn_args_t* args, fz_stream_t stream);
