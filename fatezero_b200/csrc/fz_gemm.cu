@@ -8,11 +8,12 @@
 // Reference ops replaced: models/resnet.py:57-80 (PseudoConv3d.forward), models/lora.py:46-54, nn.Linear call sites of
 // prompt_attention/attention_register.py:81,99-100,124,156-160,214 and diffusers FeedForward/GEGLU (models/attention.py:320).
 //
-// Structure (per CTA, 192 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+// Structure (per CTA, 320 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
 //   warp 0 : TMA producer   — A box {64ch, rows} + W box {64ch, BLOCK_N} per stage, SWIZZLE_128B, mbarrier complete_tx
 //   warp 1 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16  M=128 x N=BLOCK_N x K=16, fp32 accumulators in TMEM,
 //                             double-buffered accumulators (2 x BLOCK_N columns) so the epilogue overlaps the next tile
-//   warps 2-5 : epilogue    — tcgen05.ld 32x32b -> registers -> fused epilogue -> 16-byte global stores
+//   warps 2-9 : epilogue    — tcgen05.ld 32x32b -> registers -> fused epilogue -> 16-byte global stores (two warps per TMEM
+//                             lane quadrant, alternating 32-column chunks)
 #include "fz_common.cuh"
 
 #include <algorithm>
@@ -32,6 +33,8 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 struct TapGemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmC;    // output [M, N] as (cols, rows), box {32 cols, 32 rows}, SWIZZLE_64B (epilogue TMA stores)
+  int use_tma_store;  // 0 = direct 16-byte stores (fallback for odd geometries)
   int a_rank;         // 2..5
   int M, N;           // valid output rows / columns (for GEGLU: N = number of OUTPUT columns = half the GEMM columns)
   int rows_per_tile;  // <= 128; tile t covers output rows [t*rows_per_tile, ...)
@@ -62,20 +65,34 @@ struct TapGemmCfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kBTilePad = (kBTileBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kATileBytes + kBTilePad;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kEpiBytes = 8 * 2 * 2048;  // 8 epilogue warps x 2 staging slots of 32 rows x 64 B
+  static constexpr int kStagesRaw = (227 * 1024 - kEpiBytes - 1280) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output rounding):
+// 1 MUFU.RCP + 1 MUFU.EX2 + 8 FMA instead of the ~40-instruction erff() — the GEGLU epilogue was XU/ALU-bound (ncu: 24 % tensor pipe).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+__global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   using Cfg = TapGemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* epi_smem = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -90,13 +107,14 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (p.use_tma_store) tma_prefetch_desc(&p.tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], 8);
     }
     fence_mbar_init();
   }
@@ -177,7 +195,74 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
     // the v0 epilogue spent ~46 instructions per output element on per-element bound / option branches (ncu: 7 % tensor pipe
     // on K=320 GEMMs); edge tiles fall back to the generic masked path.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;  // two warps per quadrant take alternating column chunks
     const int row_in_tile = quad * 32 + lane;
+    // Coalesced output path: each warp stages its 32 rows x 32 columns (64 B rows, 64-byte swizzle => conflict-free 16-byte
+    // st.shared) and one lane issues a TMA store; direct per-row 16-byte stores touch 32 lines per instruction and made the
+    // epilogue LSU-bound (~2.4 us per 128x160 tile).
+    uint8_t* my_epi = epi_smem + (warp - 2) * 2 * 2048;
+    uint32_t epi_count = 0;
+    auto store_chunk32 = [&](const uint4 (&o)[4], long long m_row, int col, int m_warp0, uint8_t* acquired) {
+      if (p.use_tma_store) {
+        uint8_t* slot = acquired;
+        if (slot == nullptr) {
+          slot = my_epi + (epi_count & 1) * 2048;
+          if (epi_count >= 2) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+        }
+        uint8_t* rowp = slot + lane * 64;
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o[j];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmC, slot, col, m_warp0);
+          tma_store_commit();
+        }
+        ++epi_count;
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(p.out + m_row * p.ldo + col);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = o[j];
+      }
+    };
+    // Coalesced residual fetch: lane l reads the 16-byte piece (l & 3) of rows (l >> 2) + 8 i of the warp's 32 x 32 block (8 lines
+    // per instruction instead of 32), the block is transposed through the staging slot and every lane picks up its own row.
+    const int r_piece = lane & 3, r_row0 = lane >> 2;
+    auto residual_fetch = [&](const __half* R, long long ld, int m_warp0, int col, uint4 (&pre)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long rr = static_cast<long long>(m_warp0) + r_row0 + 8 * i;
+        pre[i] = (rr < p.M) ? *reinterpret_cast<const uint4*>(R + rr * ld + col + r_piece * 8) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto residual_add = [&](const uint4 (&pre)[4], uint8_t* slot, float (&v)[32]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r_row0 + 8 * i;
+        *reinterpret_cast<uint4*>(slot + r * 64 + ((r_piece ^ ((r >> 1) & 3)) << 4)) = pre[i];
+      }
+      __syncwarp();
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 x = *reinterpret_cast<const uint4*>(slot + lane * 64 + ((j ^ sw) << 4));
+        const __half2* h = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+      }
+      __syncwarp();
+    };
+    auto acquire_slot = [&]() -> uint8_t* {
+      if (epi_count >= 2) {
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+      }
+      return my_epi + (epi_count & 1) * 2048;
+    };
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -193,7 +278,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
         constexpr int CH = (HALF >= 32) ? 32 : 16;
         if constexpr (HALF >= 16) {
 #pragma unroll 1
-          for (int c = 0; c < HALF; c += CH) {
+          for (int c = half * CH; c < HALF; c += 2 * CH) {
             uint32_t xa[CH], ga[CH];
             if constexpr (CH == 32) {
               tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(xa));
@@ -204,7 +289,9 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
             }
             tmem_ld_wait();
             const int ocol0 = nt * HALF + c;
-            if (row_ok && ocol0 + CH <= p.N) {
+            const int m_warp0 = mt * p.rows_per_tile + quad * 32;
+            const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
+            if (warp_ok && ocol0 + CH <= p.N && (row_ok || (p.use_tma_store && CH == 32))) {
               float xv[CH], gv[CH];
 #pragma unroll
               for (int e = 0; e < CH; ++e) { xv[e] = __uint_as_float(xa[e]); gv[e] = __uint_as_float(ga[e]); }
@@ -218,17 +305,22 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                   gv[4 * j] += b.x; gv[4 * j + 1] += b.y; gv[4 * j + 2] += b.z; gv[4 * j + 3] += b.w;
                 }
               }
-              uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + ocol0);
+              uint4 o[CH / 8];
 #pragma unroll
               for (int j = 0; j < CH / 8; ++j) {
-                uint4 o;
                 __half2 h0 = __floats2half2_rn(xv[8 * j + 0] * gelu_erf(gv[8 * j + 0]), xv[8 * j + 1] * gelu_erf(gv[8 * j + 1]));
                 __half2 h1 = __floats2half2_rn(xv[8 * j + 2] * gelu_erf(gv[8 * j + 2]), xv[8 * j + 3] * gelu_erf(gv[8 * j + 3]));
                 __half2 h2 = __floats2half2_rn(xv[8 * j + 4] * gelu_erf(gv[8 * j + 4]), xv[8 * j + 5] * gelu_erf(gv[8 * j + 5]));
                 __half2 h3 = __floats2half2_rn(xv[8 * j + 6] * gelu_erf(gv[8 * j + 6]), xv[8 * j + 7] * gelu_erf(gv[8 * j + 7]));
-                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                op[j] = o;
+                o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
+                o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
+              }
+              if constexpr (CH == 32) {
+                store_chunk32(o, m, ocol0, m_warp0, nullptr);
+              } else {
+                uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + ocol0);
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) op[j] = o[j];
               }
             } else if (row_ok) {
 #pragma unroll
@@ -246,15 +338,20 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       } else {
         constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
         const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
+        uint4 preA[4], preB[4];
+        bool have_pre = false;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += CH) {
+        for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
           uint32_t acc[CH];
           if constexpr (CH == 32) tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(acc));
           else tmem_ld_32x32b_x16(t_row + c, reinterpret_cast<uint32_t(&)[16]>(acc));
           tmem_ld_wait();
           const int col0 = nt * BLOCK_N + c;
-          if (!row_ok || col0 >= p.N) continue;
-          if (col0 + CH <= p.N && col0 + CH <= p.vt_col_start) {
+          const int m_warp0 = mt * p.rows_per_tile + quad * 32;
+          const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
+          if (!warp_ok || col0 >= p.N) continue;
+          const bool fast = col0 + CH <= p.N && col0 + CH <= p.vt_col_start;
+          if (fast && (row_ok || (p.use_tma_store && CH == 32))) {
             // ---------------- fast path: full chunk, row-major output ----------------
             float v[CH];
 #pragma unroll
@@ -267,7 +364,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
-            if (gb) {
+            if (gb && row_ok) {
               const float4* bp = reinterpret_cast<const float4*>(gb + col0);
 #pragma unroll
               for (int j = 0; j < CH / 4; ++j) {
@@ -275,36 +372,65 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
-#pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 r = rp[j];
-                const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+            uint8_t* slot = nullptr;
+            if constexpr (CH == 32) {
+              if (p.use_tma_store && (p.residual || p.residual2)) {
+                slot = acquire_slot();
+                if (!have_pre) {
+                  if (p.residual) residual_fetch(p.residual, p.ldr, m_warp0, col0, preA);
+                  if (p.residual2) residual_fetch(p.residual2, p.ldr2, m_warp0, col0, preB);
+                }
+                if (p.residual) residual_add(preA, slot, v);
+                if (p.residual2) residual_add(preB, slot, v);
+                // software pipeline: issue the next chunk's residual loads now, consume them after its TMEM load
+                const int c_next = c + 2 * CH;
+                const int col_next = nt * BLOCK_N + c_next;
+                have_pre = c_next < BLOCK_N && col_next + CH <= p.N && col_next + CH <= p.vt_col_start;
+                if (have_pre) {
+                  if (p.residual) residual_fetch(p.residual, p.ldr, m_warp0, col_next, preA);
+                  if (p.residual2) residual_fetch(p.residual2, p.ldr2, m_warp0, col_next, preB);
+                }
               }
             }
-            if (p.residual2) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual2 + m * p.ldr2 + col0);
+            if (slot == nullptr) {
+              if (p.residual && row_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 r = rp[j];
-                const __half2* h = reinterpret_cast<const __half2*>(&r);
+                for (int j = 0; j < CH / 8; ++j) {
+                  const uint4 r = rp[j];
+                  const __half2* h = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+                  for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+                }
+              }
+              if (p.residual2 && row_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual2 + m * p.ldr2 + col0);
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) {
+                  const uint4 r = rp[j];
+                  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y; }
+                }
               }
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+            uint4 o[CH / 8];
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {
-              uint4 o;
               __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
               __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-              o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-              op[j] = o;
+              o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
+              o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
             }
+            if constexpr (CH == 32) {
+              store_chunk32(o, m, col0, m_warp0, slot);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) op[j] = o[j];
+            }
+          } else if (!row_ok) {
+            continue;
           } else if (col0 >= p.vt_col_start) {
             // ---------------- V^T store: out_vt[((bf*heads + h)*d + dd)*ld + s]; lanes = consecutive s -> 64-byte segments ----------------
             const long long bf = m / p.vt_S;
@@ -348,6 +474,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+    if (p.use_tma_store && lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -381,7 +508,7 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  tapgemm_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(p);
+  tapgemm_kernel<BN><<<grid, 320, Cfg::kSmemBytes, stream>>>(p);
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
@@ -405,6 +532,16 @@ static int pick_block_n(int gemm_cols, int mode, int forced, int m_tiles) {
 }
 
 static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cudaStream_t stream) {
+  // output tensor map for the TMA-store epilogue ([M, N_out] row-major, row stride ldo)
+  p.use_tma_store = 0;
+  if (p.rows_per_tile % 32 == 0 && p.ldo % 8 == 0 && p.N % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+      std::min(p.N, p.vt_col_start) >= 32) {
+    uint64_t dims[2] = {static_cast<uint64_t>(std::min(p.N, p.vt_col_start)), static_cast<uint64_t>(p.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(p.ldo)};
+    uint32_t box[2] = {32, 32};
+    if (int rc = encode_tmap_f16_sw(&p.tmC, p.out, 2, dims, strides, box, 64)) return rc;
+    p.use_tma_store = 1;
+  }
   const int bn = pick_block_n(gemm_cols, p.mode, forced_bn, p.m_tiles);
   p.n_tiles = (gemm_cols + bn - 1) / bn;
   switch (bn) {
