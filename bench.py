@@ -137,7 +137,7 @@ def instrument_tapgemm(pipe, x0_dev, emb_src):
             s.record(stream)
             out = fn(*a, **k)
             e.record(stream)
-            rec.append((flops_of(a, k, out), s, e))
+            rec.append((flops_of(a, k, out), s, e, (fn.__name__, tuple(a[0].shape), tuple(a[1].shape))))
             return out
         return inner
 
@@ -161,6 +161,16 @@ def instrument_tapgemm(pipe, x0_dev, emb_src):
         ops.gemm, ops.conv3x3, ops.tconv3 = saved
     flops = sum(r[0] for r in rec)
     secs = sum(r[1].elapsed_time(r[2]) for r in rec) / 1e3
+    if os.environ.get("FZ_SHAPE_REPORT"):
+        agg = {}
+        for fl, s, e, key in rec:
+            d = agg.setdefault(str(key), [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += s.elapsed_time(e)
+            d[2] += fl
+        rows = sorted(([k, v[0], v[1], v[2] / max(v[1], 1e-9) / 1e9] for k, v in agg.items()), key=lambda r: -r[2])
+        with open(os.environ["FZ_SHAPE_REPORT"], "w") as f:
+            json.dump([dict(shape=r[0], launches=r[1], ms_total=round(r[2], 2), tflops=round(r[3], 1)) for r in rows], f, indent=1)
     return flops, secs, len(rec)
 
 

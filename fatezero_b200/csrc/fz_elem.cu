@@ -36,8 +36,10 @@ constexpr int kGnMaxSlots = 4;
 
 // Statistics pass: every CTA reduces its pixel chunk of one image to per-group partial (sum, sumsq) WITHOUT atomics
 // (v0 used ~4k contended shared-memory atomics per CTA): registers -> smem [TY][C] -> per channel -> per group -> partial[nb][chunk][g].
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, int TX, int slots,
+template <int SLOTS>
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, int TX,
                                                              int px_per_cta, float2* __restrict__ partial) {
+  constexpr int slots = SLOTS;  // register arrays are sized by the template: 1 slot for C <= 2048 keeps occupancy (bytes in flight) high
   extern __shared__ float gn_smem[];  // [TY][C] sums, [TY][C] sumsq
   const int nb = blockIdx.y;
   const int CV = C / 8;
@@ -46,9 +48,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
   const int TY = kGnThreads / TX;
   float* s_sum = gn_smem;
   float* s_sq = gn_smem + TY * C;
-  float acc[kGnMaxSlots][8], acc2[kGnMaxSlots][8];
+  float acc[SLOTS][8], acc2[SLOTS][8];
 #pragma unroll
-  for (int s = 0; s < kGnMaxSlots; ++s)
+  for (int s = 0; s < SLOTS; ++s)
 #pragma unroll
     for (int e = 0; e < 8; ++e) { acc[s][e] = 0.f; acc2[s][e] = 0.f; }
   const int p0 = blockIdx.x * px_per_cta;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
 #pragma unroll 4
     for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
-      for (int s = 0; s < kGnMaxSlots; ++s) {
+      for (int s = 0; s < SLOTS; ++s) {
         const int cv = tx + s * TX;
         if (s < slots) {
           const Half8 h = *reinterpret_cast<const Half8*>(xb + static_cast<long long>(p) * C + cv * 8);
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
       }
     }
 #pragma unroll
-    for (int s = 0; s < kGnMaxSlots; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const int cv = tx + s * TX;
       if (s < slots) {
 #pragma unroll
@@ -98,10 +100,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
   }
 }
 
+template <int SLOTS>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, int C, int G,
-                                                             int frames_per_stat, int TX, int slots, int px_per_cta, int chunks,
+                                                             int frames_per_stat, int TX, int px_per_cta, int chunks,
                                                              const float2* __restrict__ partial, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int silu) {
+  constexpr int slots = SLOTS;
   __shared__ double s_red[kGnThreads][2];
   __shared__ float s_mean[64], s_rstd[64];
   const int nb = blockIdx.y;
@@ -138,9 +142,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = kGnThreads / TX;
   if (ty >= TY) return;
-  float sc[kGnMaxSlots][8], sh[kGnMaxSlots][8];
+  float sc[SLOTS][8], sh[SLOTS][8];
 #pragma unroll
-  for (int s = 0; s < kGnMaxSlots; ++s) {
+  for (int s = 0; s < SLOTS; ++s) {
     const int cv = tx + s * TX;
     if (s < slots) {
 #pragma unroll
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
 #pragma unroll 4
   for (int p = p0 + ty; p < p1; p += TY) {
 #pragma unroll
-    for (int s = 0; s < kGnMaxSlots; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const int cv = tx + s * TX;
       if (s < slots) {
         const long long off = base + static_cast<long long>(p) * C + cv * 8;
@@ -179,11 +183,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
 static void gn_geometry(int C, int HW, int NB, int* TX, int* slots, int* px_per_cta, int* chunks) {
   const int CV = C / 8;
   int s = (CV + kGnThreads - 1) / kGnThreads;
-  while (CV % s) ++s;  // TX * slots == CV exactly
+  while (CV % s || s == 3) ++s;  // TX * slots == CV exactly, slots in {1, 2, 4}
   *slots = s;
   *TX = CV / s;
   const int TY = kGnThreads / *TX;
-  int want = std::max(1, (4 * sm_count()) / std::max(1, NB));
+  int want = std::max(1, ((s == 1 ? 8 : 4) * sm_count()) / std::max(1, NB));  // 1-slot kernels use ~40 registers: 8 CTAs per SM resident
   int ppc = std::max(TY, (HW + want - 1) / want);
   *px_per_cta = ppc;
   *chunks = (HW + ppc - 1) / ppc;
@@ -194,29 +198,31 @@ static void gn_geometry(int C, int HW, int NB, int* TX, int* slots, int* px_per_
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // C <= 8*32*8 = 2048
 
-constexpr int kLnRows = 2;  // rows per warp in flight (memory-level parallelism)
+// NV = 16-byte vectors per lane (ceil(C/256)), ROWS = rows per warp in flight (memory-level parallelism); both compile-time so the
+// row buffer stays in registers and occupancy follows the real channel count.
+template <int NV, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long M, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kLnRows;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= M) return;
   const int CV = C / 8;
-  Half8 buf[kLnRows][kLnMaxVec];
-  float sum[kLnRows], sq[kLnRows];
+  Half8 buf[ROWS][NV];
+  float sum[ROWS], sq[ROWS];
 #pragma unroll
-  for (int r = 0; r < kLnRows; ++r) {
+  for (int r = 0; r < ROWS; ++r) {
     sum[r] = 0.f;
     const long long row = min(row0 + r, M - 1);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int cv = lane + i * 32;
       if (cv < CV) buf[r][i] = *reinterpret_cast<const Half8*>(x + row * C + cv * 8);
     }
   }
 #pragma unroll
-  for (int r = 0; r < kLnRows; ++r) {
+  for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (lane + i * 32 < CV) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) sum[r] += __half2float(buf[r][i].v[e]);
@@ -226,11 +232,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     for (int o = 16; o > 0; o >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
   }
 #pragma unroll
-  for (int r = 0; r < kLnRows; ++r) {
+  for (int r = 0; r < ROWS; ++r) {
     const float mean = sum[r] / C;
     sq[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (lane + i * 32 < CV) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -243,13 +249,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     for (int o = 16; o > 0; o >>= 1) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
   }
 #pragma unroll
-  for (int r = 0; r < kLnRows; ++r) {
+  for (int r = 0; r < ROWS; ++r) {
     const long long row = row0 + r;
     if (row >= M) break;
     const float mean = sum[r] / C;
     const float rstd = rsqrtf(sq[r] / C + eps);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int cv = lane + i * 32;
       if (cv < CV) {
         Half8 o;
@@ -594,14 +600,25 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
   const size_t smem = static_cast<size_t>(2) * TY * C * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   dim3 grid(chunks, NB);
   float2* partial = static_cast<float2*>(workspace_f64);
-  gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(static_cast<const __half*>(x), HW, C, groups, TX, slots, ppc, partial);
-  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(y), HW, C, groups, frames_per_stat, TX,
-                                                   slots, ppc, chunks, partial, gamma, beta, eps, silu);
+  const __half* xh = static_cast<const __half*>(x);
+  __half* yh = static_cast<__half*>(y);
+#define FZ_GN_LAUNCH(SL)                                                                                                          \
+  do {                                                                                                                             \
+    gn_stats_kernel<SL><<<grid, kGnThreads, smem, stream>>>(xh, HW, C, groups, TX, ppc, partial);                                  \
+    gn_apply_kernel<SL><<<grid, kGnThreads, 0, stream>>>(xh, yh, HW, C, groups, frames_per_stat, TX, ppc, chunks, partial, gamma, \
+                                                         beta, eps, silu);                                                         \
+  } while (0)
+  if (slots == 1) FZ_GN_LAUNCH(1);
+  else if (slots == 2) FZ_GN_LAUNCH(2);
+  else FZ_GN_LAUNCH(4);
+#undef FZ_GN_LAUNCH
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
@@ -610,8 +627,22 @@ extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, cons
                                 cudaStream_t stream) {
   FZ_CHECK_ARG(x && y && gamma && beta, "fz_layernorm: null pointer");
   FZ_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * kLnMaxVec, "fz_layernorm: C=%d unsupported", C);
-  layernorm_kernel<<<static_cast<unsigned>((M + 8 * kLnRows - 1) / (8 * kLnRows)), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(y), M, C, gamma,
-                                                                           beta, eps);
+  const int nv = (C / 8 + 31) / 32;
+  const __half* xh = static_cast<const __half*>(x);
+  __half* yh = static_cast<__half*>(y);
+#define FZ_LN_LAUNCH(NV, ROWS) \
+  layernorm_kernel<NV, ROWS><<<static_cast<unsigned>((M + 8 * ROWS - 1) / (8 * ROWS)), 256, 0, stream>>>(xh, yh, M, C, gamma, beta, eps)
+  switch (nv) {
+    case 1: FZ_LN_LAUNCH(1, 4); break;
+    case 2: FZ_LN_LAUNCH(2, 4); break;
+    case 3: FZ_LN_LAUNCH(3, 2); break;
+    case 4: FZ_LN_LAUNCH(4, 2); break;
+    case 5: FZ_LN_LAUNCH(5, 2); break;
+    case 6: FZ_LN_LAUNCH(6, 2); break;
+    case 7: FZ_LN_LAUNCH(7, 1); break;
+    default: FZ_LN_LAUNCH(8, 1); break;
+  }
+#undef FZ_LN_LAUNCH
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
