@@ -35,6 +35,7 @@ struct AttnParams {
   CUtensorMap tmQ;      // (d, heads, S_q, BF)                 box (64, 1, 128, 1)
   CUtensorMap tmK;      // (d, heads, keys_per_slot, SRC)      box (64, 1, 64, 1)
   CUtensorMap tmVt;     // (keys_ld, d, heads, SRC)            box (64, d_pad, 1, 1)
+  CUtensorMap tmK2;     // tmK with box (64, 1, 128, 1): 128-key tiles of the plain kernel
   CUtensorMap tmStore;  // (keys_ld_cache, slots, S_q, heads, Fc) box (64, 1, 128, 1, 1)   cache slab written (STORE)
   CUtensorMap tmBase;   // same geometry, cache slab read (REPLACE / BLEND)
   int S_q;              // queries per (frame, head)
@@ -635,6 +636,274 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Plain attention (no controller hook on any row) for head dims <= 64: the 64x64-latent spatio-temporal self-attention layers
+// (attention_register.py:131-218 with q.shape[1] > 32**2, which the controller leaves untouched: attention_store.py:58-59), i.e.
+// 3/4 of the attention time of a DDIM step.  Same arithmetic as attn_kernel's FZ_ATTN_NONE rows (pass 1 row max, pass 2
+// p = exp2(s*c - m*c) rounded to fp16 for PV, fp32 row sum, O / l at the end) on a pipeline built for the small head dim:
+//   * key tiles of 128 (QK^T as M128 x N128 UMMAs: with N=64 the A operand re-read from shared memory, not the math, bounds the MMA)
+//   * P never touches shared memory: the softmax warps overwrite the S columns in TMEM with packed fp16 (tcgen05.st) and the PV
+//     UMMA takes its A operand from TMEM -> no swizzled st.shared (bank conflicts), no proxy fence, 1/3 of the smem operand traffic
+//   * three S/P buffers rotate over two softmax warpgroups (tile j -> buffer j % 3, warpgroup j & 1); tcgen05.mma executes in
+//     issue order, so QK(j+3) is simply issued behind PV(j) into the buffer it frees: pass 2 needs no "S empty" barrier at all
+//   * PV k-steps alternate between two O accumulators (two independent accumulate chains), summed in the epilogue.
+// TMEM: S/P buffers at columns 0 / 128 / 256, O0 at 384, O1 at 448.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPlainStageBytes = 16384;
+constexpr int kPlainStages = 8;
+constexpr int kPlainSmem = 1024 + kAtomBytes + kPlainStages * kPlainStageBytes + 2048;
+
+__global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int bf = blockIdx.z;
+
+  uint8_t* s_q = smem;
+  uint8_t* s_ring = s_q + kAtomBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kPlainStages * kPlainStageBytes);
+  uint64_t* ring_full = bars;                     // [8]
+  uint64_t* ring_empty = bars + kPlainStages;     // [8]
+  uint64_t* q_full = bars + 2 * kPlainStages;
+  uint64_t* s_full = q_full + 1;                  // [3]
+  uint64_t* s_empty = s_full + 3;                 // [3] (pass 1 only)
+  uint64_t* p_full = s_empty + 3;                 // [3]
+  uint64_t* o_full = p_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xchg = reinterpret_cast<float*>(o_full + 2);  // [2 warpgroups][128 rows]
+
+  const int tiles_per_slot = p.keys_per_slot >> 7;
+  const int n_tiles = tiles_per_slot * p.n_slots;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK2);
+    tma_prefetch_desc(&p.tmVt);
+    for (int s = 0; s < kPlainStages; ++s) {
+      mbar_init(&ring_full[s], 1);
+      mbar_init(&ring_empty[s], 1);
+    }
+    mbar_init(q_full, 1);
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 4);
+      mbar_init(&p_full[b], 4);
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o0 = tmem_base + 384, tmem_o1 = tmem_base + 448;
+  const int vt_atom_bytes = p.d_pad * 128;
+
+  if (warp == 8) {
+    // =========================================== TMA producer ===========================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == kPlainStages) { stage = 0; phase ^= 1; } };
+      auto load_k = [&](int j) {
+        const int slot = j / tiles_per_slot, k0 = (j - slot * tiles_per_slot) << 7;
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], 128 * 128);
+        tma_load_4d(s_ring + stage * kPlainStageBytes, &p.tmK2, &ring_full[stage], 0, head, k0, p.src_index[slot][bf]);
+        advance();
+      };
+      auto load_v = [&](int j) {
+        const int slot = j / tiles_per_slot, k0 = (j - slot * tiles_per_slot) << 7;
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], 2 * vt_atom_bytes);
+        uint8_t* dst = s_ring + stage * kPlainStageBytes;
+        tma_load_4d(dst, &p.tmVt, &ring_full[stage], k0, 0, head, p.src_index[slot][bf]);
+        tma_load_4d(dst + vt_atom_bytes, &p.tmVt, &ring_full[stage], k0 + 64, 0, head, p.src_index[slot][bf]);
+        advance();
+      };
+      mbar_expect_tx(q_full, kAtomBytes);
+      tma_load_4d(s_q, &p.tmQ, q_full, 0, head, q0, bf);
+      for (int j = 0; j < n_tiles; ++j) load_k(j);                 // pass 1
+      for (int j = 0; j < min(3, n_tiles); ++j) load_k(j);         // pass 2: same order as the MMA warp consumes
+      for (int j = 0; j < n_tiles; ++j) {
+        load_v(j);
+        if (j + 3 < n_tiles) load_k(j + 3);
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================== MMA issuer ===========================================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc_s = umma_idesc_f16(128, 128);
+    const uint32_t idesc_o = umma_idesc_f16(128, p.d_pad);
+    const uint64_t desc_hi = umma_desc_k_sw128(0);
+    const uint32_t ring_lo0 = (smem_u32(s_ring) & 0x3FFFF) >> 4;
+    const uint32_t q_lo = (smem_u32(s_q) & 0x3FFFF) >> 4;
+    const uint32_t vt_atom_lo = static_cast<uint32_t>(vt_atom_bytes) >> 4;
+    uint32_t ring_lo = ring_lo0;
+    auto advance = [&]() {
+      ring_lo += kPlainStageBytes >> 4;
+      if (++stage == kPlainStages) { stage = 0; phase ^= 1; ring_lo = ring_lo0; }
+    };
+    const int ksteps = (p.d + 15) >> 4;
+    auto issue_qk = [&](int b) {
+      mbar_wait(&ring_full[stage], phase);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < ksteps) umma_f16_ss(tmem_base + b * 128, desc_hi | (q_lo + 2 * k), desc_hi | (ring_lo + 2 * k), idesc_s, k ? 1u : 0u);
+        umma_commit(&ring_empty[stage]);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+      advance();
+    };
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    for (int j = 0; j < n_tiles; ++j) {  // pass 1
+      const int b = j % 3;
+      if (j >= 3) {
+        mbar_wait(&s_empty[b], ((j / 3) - 1) & 1);
+        tc_fence_after();
+      }
+      issue_qk(b);
+    }
+    for (int j = 0; j < min(3, n_tiles); ++j) {  // pass 2 prologue: the buffers' last pass-1 scores must have been read
+      const int uses1 = (n_tiles + 2 - j) / 3;
+      mbar_wait(&s_empty[j], (uses1 - 1) & 1);
+      tc_fence_after();
+      issue_qk(j);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j % 3;
+      mbar_wait(&p_full[b], (j / 3) & 1);
+      mbar_wait(&ring_full[stage], phase);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a0 = tmem_base + b * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t bdesc = desc_hi | (ring_lo + (k >> 2) * vt_atom_lo + 2 * (k & 3));
+          umma_f16_ts((k & 1) ? tmem_o1 : tmem_o0, a0 + k * 8, bdesc, idesc_o, (j | (k >> 1)) ? 1u : 0u);
+        }
+        umma_commit(&ring_empty[stage]);
+      }
+      __syncwarp();
+      advance();
+      if (j + 3 < n_tiles) issue_qk(b);  // executes behind PV(j) on the tensor pipe: reuses the buffer PV(j) just read
+    }
+    if (leader) umma_commit(o_full);
+    __syncwarp();
+  } else {
+    // =========================================== softmax / epilogue warpgroups ===========================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const int wg = warp >> 2;
+    const float sc2 = p.scale_log2;
+    float m_run = -INFINITY;
+    for (int j = wg; j < n_tiles; j += 2) {  // pass 1: row max
+      const int b = j % 3;
+      mbar_wait(&s_full[b], (j / 3) & 1);
+      tc_fence_after();
+      const uint32_t sbase = tmem_base + lane_addr + b * 128;
+      float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(sbase + h * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+        tmem_ld_32x32b_x32(sbase + h * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 64; e += 8) {
+          c0 = fmaxf(fmaxf(c0, __uint_as_float(r[e + 0])), __uint_as_float(r[e + 1]));
+          c1 = fmaxf(fmaxf(c1, __uint_as_float(r[e + 2])), __uint_as_float(r[e + 3]));
+          c2 = fmaxf(fmaxf(c2, __uint_as_float(r[e + 4])), __uint_as_float(r[e + 5]));
+          c3 = fmaxf(fmaxf(c3, __uint_as_float(r[e + 6])), __uint_as_float(r[e + 7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+      m_run = fmaxf(m_run, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
+    }
+    // merge the warpgroups' maxima; the barrier also orders every pass-1 phase of s_full before the pass-2 waits
+    xchg[wg * 128 + row] = m_run;
+    named_bar_sync(3, 256);
+    m_run = fmaxf(m_run, xchg[(wg ^ 1) * 128 + row]);
+    named_bar_sync(3, 256);
+    const float mb2 = m_run * sc2;
+    float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lf3 = 0.f;
+    for (int j = wg; j < n_tiles; j += 2) {  // pass 2: probabilities, written back over the scores as packed fp16
+      const int b = j % 3;
+      const int uses1 = (n_tiles + 2 - b) / 3;
+      mbar_wait(&s_full[b], (uses1 + j / 3) & 1);
+      tc_fence_after();
+      const uint32_t sbase = tmem_base + lane_addr + b * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[64];
+        tmem_ld_32x32b_x32(sbase + h * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+        tmem_ld_32x32b_x32(sbase + h * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+        tmem_ld_wait();
+        float* pv = reinterpret_cast<float*>(r);
+#pragma unroll
+        for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pk[e] = pack_half2(pv[2 * e], pv[2 * e + 1]);
+        tmem_st_32x32b_x32(sbase + h * 32, pk);  // keys [64h, 64h+64) -> columns [32h, 32h+32): already-read score columns
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+    float l_run = (lf0 + lf1) + (lf2 + lf3);
+    xchg[wg * 128 + row] = l_run;
+    named_bar_sync(3, 256);
+    l_run += xchg[(wg ^ 1) * 128 + row];
+    // epilogue: (O0 + O1) / l -> fp16 -> global; 16-column chunks alternate between the warpgroups
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float o_scale = 1.0f / l_run;
+    __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + q0 + row) * p.ldo + head * p.d;
+    for (int c = wg * 16; c < p.d_pad; c += 32) {
+      uint32_t r[16], r1[16];
+      tmem_ld_32x32b_x16(tmem_o0 + lane_addr + c, r);
+      tmem_ld_32x32b_x16(tmem_o1 + lane_addr + c, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; e += 8) {
+        if (c + e < p.d) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = (__uint_as_float(r[e + i]) + __uint_as_float(r1[e + i])) * o_scale;
+          uint4 v;
+          v.x = pack_half2(o[0], o[1]);
+          v.y = pack_half2(o[2], o[3]);
+          v.z = pack_half2(o[4], o[5]);
+          v.w = pack_half2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(orow + c + e) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace fz
 
 using namespace fz;
@@ -692,6 +961,25 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     uint32_t box[4] = {64, (uint32_t)p.d_pad, 1, 1};
     if (int rc = encode_tmap_f16(&p.tmVt, a->vt, 4, dims, strides, box, true)) return rc;
   }
+  // rows without any controller hook and a small head dim take the TMEM-resident-P kernel
+  const bool plain = (a->row_mode == FZ_ATTN_NONE || a->edit_bf_start >= a->BF) && !a->acc && a->d <= 64 && a->keys_per_slot % 128 == 0 &&
+                     a->S_q % 128 == 0;
+  if (plain) {
+    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->keys_per_slot, (uint64_t)a->n_src};
+    uint64_t strides[3] = {(uint64_t)a->d, (uint64_t)a->ldk, (uint64_t)a->ldk * a->keys_per_slot};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (int rc = encode_tmap_f16(&p.tmK2, a->k, 4, dims, strides, box, true)) return rc;
+    static bool configured_plain = false;
+    if (!configured_plain) {
+      FZ_CUDA(cudaFuncSetAttribute(attn_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem));
+      configured_plain = true;
+    }
+    dim3 grid(a->S_q / 128, a->heads, a->BF);
+    attn_plain_kernel<<<grid, 320, kPlainSmem, stream>>>(p);
+    FZ_CUDA(cudaGetLastError());
+    return FZ_OK;
+  }
+  p.tmK2 = p.tmK;
   // cache geometry: a row of the slab is n_slots * keys_ld_slot wide, keys_ld_slot = cache_ld / n_slots
   if (a->store) {
     if (int rc = encode_cache_map(&p.tmStore, a->store, (int)(a->cache_ld / a->n_slots), a->n_slots, a->S_q, a->heads, Fc, a->cache_ld)) return rc;

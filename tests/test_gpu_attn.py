@@ -63,6 +63,12 @@ SELF_CASES = [
     (4, 4, 256, 4, 16, "prev_first"),
     (2, 2, 144, 4, 80, "prev_first"),
     (2, 2, 576, 2, 64, "mid"),
+    # TMEM-resident-P kernel (no hook, d <= 64, 128-key tiles): 1, 3, 5 and 10 key tiles, odd / even, one and two K/V frames
+    (2, 2, 128, 2, 40, "own"),
+    (3, 3, 384, 2, 48, "mid"),
+    (2, 2, 640, 1, 40, "own"),
+    (2, 2, 640, 2, 64, "prev_first"),
+    (2, 2, 1024, 8, 40, "prev_first"),
 ]
 
 

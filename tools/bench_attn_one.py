@@ -11,6 +11,8 @@ C_ = heads * d
 q = torch.randn(BF * S, C_, device=dev).half(); k = torch.randn(BF * S, C_, device=dev).half()
 vt = torch.randn(BF, heads, d, S, device=dev).half(); out = torch.empty(BF * S, C_, device=dev, dtype=torch.float16)
 si = [[(b * 8 + 3) for b in range(BF // 8) for f in range(8)]] if BF >= 8 else [list(range(BF))]
+if os.environ.get("SLOTS", "1") == "2":  # the real sparse-causal pattern: [previous frame, first frame]
+    si = [[b * 8 + max(f - 1, 0) for b in range(BF // 8) for f in range(8)], [b * 8 for b in range(BF // 8) for f in range(8)]]
 kw = dict(S_q=S, keys_per_slot=S, n_src=BF, d=d, heads=heads, F=min(8, BF), BF=BF, scale=d ** -0.5, src_index=si)
 cache = torch.empty(BF, heads, S, S, device=dev, dtype=torch.float16) if mode != "none" else None
 if mode == "replace":
@@ -26,7 +28,7 @@ s.record()
 for _ in range(5): fn()
 e.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(e) / 5
-print(dict(S=S, d=d, mode=mode, ms=ms, tflops=4 * BF * heads * S * S * d / ms / 1e9))
+print(dict(S=S, d=d, mode=mode, ms=ms, tflops=4 * BF * heads * S * S * len(si) * d / ms / 1e9))
 dbg = torch.zeros(32, dtype=torch.int64, device=dev)
 kw["dbg"] = dbg
 fn(); torch.cuda.synchronize()
