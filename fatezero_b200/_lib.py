@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfatezero_b200.so")
+# FZ_LIB_VARIANT=<suffix> loads libfatezero_b200_<suffix>.so: a development aid for A/B-ing kernel variants built with
+# `python fatezero_b200/_build.py --variant <suffix> --flags "-D..."` inside one GPU session (never set by the product path).
+_VARIANT = os.environ.get("FZ_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libfatezero_b200_{_VARIANT}.so" if _VARIANT else "libfatezero_b200.so")
 
 c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 

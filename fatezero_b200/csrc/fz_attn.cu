@@ -639,19 +639,27 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
 // ---------------------------------------------------------------------------------------------------------------
 // Plain attention (no controller hook on any row) for head dims <= 64: the 64x64-latent spatio-temporal self-attention layers
 // (attention_register.py:131-218 with q.shape[1] > 32**2, which the controller leaves untouched: attention_store.py:58-59), i.e.
-// 3/4 of the attention time of a DDIM step.  Same arithmetic as attn_kernel's FZ_ATTN_NONE rows (pass 1 row max, pass 2
-// p = exp2(s*c - m*c) rounded to fp16 for PV, fp32 row sum, O / l at the end) on a pipeline built for the small head dim:
-//   * key tiles of 128 (QK^T as M128 x N128 UMMAs: with N=64 the A operand re-read from shared memory, not the math, bounds the MMA)
+// 3/4 of the attention time of a DDIM step.  Nothing has to be stored or edited here, so the probabilities need not be
+// normalised before PV: ONE pass over the keys with a running row maximum (online softmax),
+//   p = exp2(s*c - m_ref*c) rounded to fp16 for PV (fp32 row sum l), O / l at the end,
+// where m_ref is the row's reference maximum.  It is only raised (and O, l rescaled by 2^((m_old - m_new) c)) when a tile's maximum
+// exceeds it by more than 8 in the log2 domain, so the rescale is rare and p <= 2^8 stays far inside fp16 range; the result is the
+// same softmax(QK^T)V, the fp16 rounding of p merely happens at a power-of-two different scale.
+// Pipeline (built for the small head dim, where the MMA issue rate and shared-memory operand reads bound the tensor pipe):
+//   * key tiles of 128: QK^T as M128 x N128 UMMAs (with N=64 the A operand re-read from shared memory bounds the MMA: measured
+//     48 clk per N=64 K=16 instruction instead of 32, tools/micro/umma_rate.cu)
 //   * P never touches shared memory: the softmax warps overwrite the S columns in TMEM with packed fp16 (tcgen05.st) and the PV
-//     UMMA takes its A operand from TMEM -> no swizzled st.shared (bank conflicts), no proxy fence, 1/3 of the smem operand traffic
-//   * three S/P buffers rotate over two softmax warpgroups (tile j -> buffer j % 3, warpgroup j & 1); tcgen05.mma executes in
-//     issue order, so QK(j+3) is simply issued behind PV(j) into the buffer it frees: pass 2 needs no "S empty" barrier at all
-//   * PV k-steps alternate between two O accumulators (two independent accumulate chains), summed in the epilogue.
-// TMEM: S/P buffers at columns 0 / 128 / 256, O0 at 384, O1 at 448.
+//     UMMA takes its A operand from TMEM (measured 24 clk per N=48 instruction instead of 44 from shared memory)
+//   * three S/P buffers rotate over two softmax warpgroups (tile j -> buffer j % 3, warpgroup j & 1).  Each warpgroup owns its own
+//     (m_ref, l, O accumulator): a rescale touches only the warpgroup's own O between two of its own PV MMAs, and the two partial
+//     results are merged in the epilogue (split-KV).  tcgen05.mma executes in issue order, so QK(j+3) is issued right behind PV(j)
+//     into the buffer it frees: no "S empty" barrier.
+// TMEM: S/P buffers at columns 0 / 128 / 256, O of warpgroup 0 at 384, of warpgroup 1 at 448.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPlainStageBytes = 16384;
-constexpr int kPlainStages = 8;
-constexpr int kPlainSmem = 1024 + kAtomBytes + kPlainStages * kPlainStageBytes + 2048;
+constexpr int kPlainStages = 10;
+constexpr int kPlainSmem = 1024 + kAtomBytes + kPlainStages * kPlainStageBytes + 4096;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -664,15 +672,15 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   uint8_t* s_q = smem;
   uint8_t* s_ring = s_q + kAtomBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kPlainStages * kPlainStageBytes);
-  uint64_t* ring_full = bars;                     // [8]
-  uint64_t* ring_empty = bars + kPlainStages;     // [8]
+  uint64_t* ring_full = bars;                     // [kPlainStages]
+  uint64_t* ring_empty = bars + kPlainStages;     // [kPlainStages]
   uint64_t* q_full = bars + 2 * kPlainStages;
   uint64_t* s_full = q_full + 1;                  // [3]
-  uint64_t* s_empty = s_full + 3;                 // [3] (pass 1 only)
-  uint64_t* p_full = s_empty + 3;                 // [3]
-  uint64_t* o_full = p_full + 3;
+  uint64_t* p_full = s_full + 3;                  // [3]
+  uint64_t* pv_done = p_full + 3;                 // [2] one per warpgroup: its latest PV has been accumulated
+  uint64_t* o_full = pv_done + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* xchg = reinterpret_cast<float*>(o_full + 2);  // [2 warpgroups][128 rows]
+  float* xchg = reinterpret_cast<float*>(o_full + 2);  // [2 warpgroups][128 rows][2]
 
   const int tiles_per_slot = p.keys_per_slot >> 7;
   const int n_tiles = tiles_per_slot * p.n_slots;
@@ -688,9 +696,10 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
     mbar_init(q_full, 1);
     for (int b = 0; b < 3; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 4);
       mbar_init(&p_full[b], 4);
     }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -699,8 +708,15 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o0 = tmem_base + 384, tmem_o1 = tmem_base + 448;
+  const uint32_t tmem_o = tmem_base + 384;  // + 64 * warpgroup
   const int vt_atom_bytes = p.d_pad * 128;
+#ifdef FZ_ATTN_PROFILE
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;  // warp-uniform
+#else
+  constexpr bool dbg_on = false;
+#endif
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
 
   if (warp == 8) {
     // =========================================== TMA producer ===========================================
@@ -726,8 +742,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
       };
       mbar_expect_tx(q_full, kAtomBytes);
       tma_load_4d(s_q, &p.tmQ, q_full, 0, head, q0, bf);
-      for (int j = 0; j < n_tiles; ++j) load_k(j);                 // pass 1
-      for (int j = 0; j < min(3, n_tiles); ++j) load_k(j);         // pass 2: same order as the MMA warp consumes
+      for (int j = 0; j < min(3, n_tiles); ++j) load_k(j);  // same order as the MMA warp consumes
       for (int j = 0; j < n_tiles; ++j) {
         load_v(j);
         if (j + 3 < n_tiles) load_k(j + 3);
@@ -751,7 +766,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
     };
     const int ksteps = (p.d + 15) >> 4;
     auto issue_qk = [&](int b) {
-      mbar_wait(&ring_full[stage], phase);
+      FZ_TIMED(1, mbar_wait(&ring_full[stage], phase));
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -765,40 +780,35 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
     };
     mbar_wait(q_full, 0);
     tc_fence_after();
-    for (int j = 0; j < n_tiles; ++j) {  // pass 1
-      const int b = j % 3;
-      if (j >= 3) {
-        mbar_wait(&s_empty[b], ((j / 3) - 1) & 1);
-        tc_fence_after();
-      }
-      issue_qk(b);
-    }
-    for (int j = 0; j < min(3, n_tiles); ++j) {  // pass 2 prologue: the buffers' last pass-1 scores must have been read
-      const int uses1 = (n_tiles + 2 - j) / 3;
-      mbar_wait(&s_empty[j], (uses1 - 1) & 1);
-      tc_fence_after();
-      issue_qk(j);
-    }
+    for (int j = 0; j < min(3, n_tiles); ++j) issue_qk(j);
+    int b = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      const int b = j % 3;
-      mbar_wait(&p_full[b], (j / 3) & 1);
-      mbar_wait(&ring_full[stage], phase);
+      const int wg = j & 1;
+      FZ_TIMED(2, mbar_wait(&p_full[b], (j / 3) & 1));
+      FZ_TIMED(3, mbar_wait(&ring_full[stage], phase));
       tc_fence_after();
       if (leader) {
         const uint32_t a0 = tmem_base + b * 128;
+        const uint32_t od = tmem_o + wg * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t bdesc = desc_hi | (ring_lo + (k >> 2) * vt_atom_lo + 2 * (k & 3));
-          umma_f16_ts((k & 1) ? tmem_o1 : tmem_o0, a0 + k * 8, bdesc, idesc_o, (j | (k >> 1)) ? 1u : 0u);
+          umma_f16_ts(od, a0 + k * 8, bdesc, idesc_o, (j >= 2 || k) ? 1u : 0u);
         }
         umma_commit(&ring_empty[stage]);
+        umma_commit(&pv_done[wg]);
       }
       __syncwarp();
       advance();
       if (j + 3 < n_tiles) issue_qk(b);  // executes behind PV(j) on the tensor pipe: reuses the buffer PV(j) just read
+      b = (b == 2) ? 0 : b + 1;
     }
     if (leader) umma_commit(o_full);
     __syncwarp();
+    if (dbg_on && leader) {
+      for (int i = 0; i < 4; ++i) p.dbg[i] = dbg_acc[i];
+      p.dbg[4] = clock64() - dbg_t0;
+    }
   } else {
     // =========================================== softmax / epilogue warpgroups ===========================================
     const int quad = warp & 3;
@@ -806,86 +816,117 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int wg = warp >> 2;
     const float sc2 = p.scale_log2;
-    float m_run = -INFINITY;
-    for (int j = wg; j < n_tiles; j += 2) {  // pass 1: row max
-      const int b = j % 3;
-      mbar_wait(&s_full[b], (j / 3) & 1);
-      tc_fence_after();
-      const uint32_t sbase = tmem_base + lane_addr + b * 128;
-      float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(sbase + h * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
-        tmem_ld_32x32b_x32(sbase + h * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 64; e += 8) {
-          c0 = fmaxf(fmaxf(c0, __uint_as_float(r[e + 0])), __uint_as_float(r[e + 1]));
-          c1 = fmaxf(fmaxf(c1, __uint_as_float(r[e + 2])), __uint_as_float(r[e + 3]));
-          c2 = fmaxf(fmaxf(c2, __uint_as_float(r[e + 4])), __uint_as_float(r[e + 5]));
-          c3 = fmaxf(fmaxf(c3, __uint_as_float(r[e + 6])), __uint_as_float(r[e + 7]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
-      m_run = fmaxf(m_run, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
-    }
-    // merge the warpgroups' maxima; the barrier also orders every pass-1 phase of s_full before the pass-2 waits
-    xchg[wg * 128 + row] = m_run;
-    named_bar_sync(3, 256);
-    m_run = fmaxf(m_run, xchg[(wg ^ 1) * 128 + row]);
-    named_bar_sync(3, 256);
-    const float mb2 = m_run * sc2;
+    const uint32_t my_o = tmem_o + wg * 64 + lane_addr;
+    float m_ref = -INFINITY;
     float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lf3 = 0.f;
-    for (int j = wg; j < n_tiles; j += 2) {  // pass 2: probabilities, written back over the scores as packed fp16
+    int t = 0;  // tiles this warpgroup has finished
+    for (int j = wg; j < n_tiles; j += 2, ++t) {
       const int b = j % 3;
-      const int uses1 = (n_tiles + 2 - b) / 3;
-      mbar_wait(&s_full[b], (uses1 + j / 3) & 1);
+      FZ_TIMED(1, mbar_wait(&s_full[b], (j / 3) & 1));
       tc_fence_after();
       const uint32_t sbase = tmem_base + lane_addr + b * 128;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(sbase + h * 64, reinterpret_cast<uint32_t(&)[32]>(r[0]));
-        tmem_ld_32x32b_x32(sbase + h * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+      uint32_t ra[32], rb[32];
+      // ---- tile maximum (TMEM reads are cheap: the scores are read again below instead of being kept in 128 registers) ----
+      {
+        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+        tmem_ld_32x32b_x32(sbase, ra);
         tmem_ld_wait();
-        float* pv = reinterpret_cast<float*>(r);
 #pragma unroll
-        for (int e = 0; e < 64; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+        for (int i = 0; i < 4; ++i) {
+          uint32_t(&cur)[32] = (i & 1) ? rb : ra;
+          uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
+          if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
 #pragma unroll
-        for (int e = 0; e < 64; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
-        uint32_t pk[32];
+          for (int e = 0; e < 32; e += 8) {
+            c0 = fmaxf(fmaxf(c0, __uint_as_float(cur[e + 0])), __uint_as_float(cur[e + 1]));
+            c1 = fmaxf(fmaxf(c1, __uint_as_float(cur[e + 2])), __uint_as_float(cur[e + 3]));
+            c2 = fmaxf(fmaxf(c2, __uint_as_float(cur[e + 4])), __uint_as_float(cur[e + 5]));
+            c3 = fmaxf(fmaxf(c3, __uint_as_float(cur[e + 6])), __uint_as_float(cur[e + 7]));
+          }
+          if (i < 3) tmem_ld_wait();
+        }
+        const float tmax = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
+        // first chunk of the exp pass goes in flight before the (rare) rescale
+        tmem_ld_32x32b_x32(sbase, ra);
+        if (t == 0) {
+          m_ref = tmax;
+        } else {
+          const bool need = (tmax - m_ref) * sc2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // this warpgroup's previous PV must have been accumulated; nothing else touches its O until p_full below
+            FZ_TIMED(0, mbar_wait(&pv_done[wg], (t - 1) & 1));
+            tc_fence_after();
+            const float m_new = need ? tmax : m_ref;
+            const float f = ex2((m_ref - m_new) * sc2);
+            m_ref = m_new;
+            lf0 *= f; lf1 *= f; lf2 *= f; lf3 *= f;
+            for (int c = 0; c < p.d_pad; c += 16) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(my_o + c, o);
+              tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) pk[e] = pack_half2(pv[2 * e], pv[2 * e + 1]);
-        tmem_st_32x32b_x32(sbase + h * 32, pk);  // keys [64h, 64h+64) -> columns [32h, 32h+32): already-read score columns
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+              tmem_st_32x32b_x16(my_o + c, o);
+            }
+          }
+        }
+        tmem_ld_wait();
+      }
+      const float mb2 = m_ref * sc2;
+      // ---- probabilities: 32-column chunks, software pipelined (load of chunk i+1 in flight during FFMA -> MUFU -> pack of chunk i);
+      //      keys [32i, 32i+32) -> packed columns [16i, 16i+16), which lie inside score columns that were already read ----
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t(&cur)[32] = (i & 1) ? rb : ra;
+        uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
+        if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
+        float* pv = reinterpret_cast<float*>(cur);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack_half2(pv[2 * e], pv[2 * e + 1]);
+        tmem_st_32x32b_x16(sbase + i * 16, pk);
+        if (i < 3) tmem_ld_wait();
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
     }
-    float l_run = (lf0 + lf1) + (lf2 + lf3);
-    xchg[wg * 128 + row] = l_run;
+    dbg_acc[7] = clock64() - dbg_t0;  // end of the key loop
+    // ---- merge the two warpgroups' partial softmax (split-KV): O = (fA O_A + fB O_B) / (fA l_A + fB l_B) ----
+    const float l_own = (lf0 + lf1) + (lf2 + lf3);
+    xchg[(wg * 128 + row) * 2 + 0] = m_ref;
+    xchg[(wg * 128 + row) * 2 + 1] = l_own;
     named_bar_sync(3, 256);
-    l_run += xchg[(wg ^ 1) * 128 + row];
-    // epilogue: (O0 + O1) / l -> fp16 -> global; 16-column chunks alternate between the warpgroups
-    mbar_wait(o_full, 0);
+    const float m_a = xchg[row * 2], l_a = xchg[row * 2 + 1];
+    const float m_b = xchg[(128 + row) * 2], l_b = xchg[(128 + row) * 2 + 1];
+    const bool has_b = n_tiles >= 2;
+    const float m_all = has_b ? fmaxf(m_a, m_b) : m_a;
+    float f_a = ex2((m_a - m_all) * sc2), f_b = has_b ? ex2((m_b - m_all) * sc2) : 0.f;
+    const float inv = 1.0f / (f_a * l_a + f_b * l_b);
+    f_a *= inv;
+    f_b *= inv;
+    FZ_TIMED(2, mbar_wait(o_full, 0));
     tc_fence_after();
-    const float o_scale = 1.0f / l_run;
     __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + q0 + row) * p.ldo + head * p.d;
-    for (int c = wg * 16; c < p.d_pad; c += 32) {
+    for (int c = wg * 16; c < p.d_pad; c += 32) {  // 16-column chunks alternate between the warpgroups
       uint32_t r[16], r1[16];
-      tmem_ld_32x32b_x16(tmem_o0 + lane_addr + c, r);
-      tmem_ld_32x32b_x16(tmem_o1 + lane_addr + c, r1);
+      tmem_ld_32x32b_x16(tmem_o + lane_addr + c, r);
+      if (has_b) tmem_ld_32x32b_x16(tmem_o + 64 + lane_addr + c, r1);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; e += 8) {
         if (c + e < p.d) {
           float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = (__uint_as_float(r[e + i]) + __uint_as_float(r1[e + i])) * o_scale;
+          for (int i = 0; i < 8; ++i) {
+            o[i] = __uint_as_float(r[e + i]) * f_a;
+            if (has_b) o[i] = fmaf(__uint_as_float(r1[e + i]), f_b, o[i]);
+          }
           uint4 v;
           v.x = pack_half2(o[0], o[1]);
           v.y = pack_half2(o[2], o[3]);
@@ -894,6 +935,11 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
           *reinterpret_cast<uint4*>(orow + c + e) = v;
         }
       }
+    }
+    if (dbg_on && lane == 0 && (warp == 0 || warp == 4)) {
+      const int base = warp == 0 ? 8 : 16;
+      for (int i = 0; i < 8; ++i) p.dbg[base + i] = dbg_acc[i];
+      p.dbg[base + 3] = clock64() - dbg_t0;
     }
   }
   tc_fence_before();

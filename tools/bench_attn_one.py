@@ -33,6 +33,7 @@ dbg = torch.zeros(32, dtype=torch.int64, device=dev)
 kw["dbg"] = dbg
 fn(); torch.cuda.synchronize()
 v = dbg.tolist()
+print("raw dbg: MMA", v[0:5], "WG A", v[8:16], "WG B", v[16:24], "QK issue: fence, mma, commit, tail", v[24:28])
 print("MMA thread : wait s_empty %d, ring_full(S) %d, p_full %d, ring_full(V) %d, total %d" % tuple(v[0:5]))
 for name, b in (("WG A", 8), ("WG B", 16)):
     print(name, ": wait s_full(p1) %d, s_full(p2) %d, p_empty %d, bar1 %d, bar2 %d, o_full %d, end_pass2 %d, total %d" % tuple(v[b:b + 8]))
