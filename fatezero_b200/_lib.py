@@ -99,9 +99,16 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+# FZ_ABLATE=<entry point>[,<entry point>...]: timing-only development aid (tools/ablate.py) — the named entry points return without
+# launching, so the wall-clock delta of a clip is that kernel class's in-situ cost.  Results are garbage; never set by the product.
+_ABLATE = frozenset(x for x in os.environ.get("FZ_ABLATE", "").split(",") if x)
+
+
 def call(name: str, *args):
     global launch_count, kernel_launches
     lib = load()
+    if _ABLATE and name in _ABLATE:
+        return
     launch_count += 1
     kernel_launches += KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib, name)(*args), name)

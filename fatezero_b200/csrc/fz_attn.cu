@@ -69,6 +69,21 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^y for y <= ~8 on the FMA / ALU pipes (no MUFU): floor via a round-down magic-number add, degree-4 minimax polynomial for the
+// fraction (max relative error 2.7e-6, far below the fp16 rounding of the probability), exponent inserted with integer arithmetic.
+// The plain attention kernel is MUFU-bound (16 ex2 / clk / SM, tools/micro/exp_rate.cu), so a quarter of its exponentials take this
+// path (measured: 20.5 exp / clk / SM for the 3:1 mix).
+__device__ __forceinline__ float ex2_poly(float y) {
+  float yr = __fadd_rd(y, 12582912.f);          // 1.5 * 2^23 + floor(y)
+  yr = fmaxf(yr, 12582912.f - 125.f);           // results below 2^-125 are flushed (fp16 rounds them to zero anyway)
+  const float fl = yr - 12582912.f;
+  const float f = y - fl;                       // [0, 1)
+  float p = fmaf(0.013534133322536945f, f, 0.05201148986816406f);
+  p = fmaf(p, f, 0.24144276976585388f);
+  p = fmaf(p, f, 0.6930038332939148f);
+  p = fmaf(p, f, 1.0000026226043701f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(yr) << 23));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // Optional in-kernel cycle accounting (compile with -DFZ_ATTN_PROFILE): adds clock reads around the waits of CTA (0,0,0).
@@ -114,6 +129,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y;
   const int bf = blockIdx.z;
@@ -172,6 +188,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
   const uint32_t tmem_o = tmem_base + 256;
 #ifdef FZ_ATTN_PROFILE
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;  // warp-uniform
@@ -665,6 +682,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y;
   const int bf = blockIdx.z;
@@ -708,6 +726,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
   const uint32_t tmem_o = tmem_base + 384;  // + 64 * warpgroup
   const int vt_atom_bytes = p.d_pad * 128;
 #ifdef FZ_ATTN_PROFILE
@@ -882,7 +901,10 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
         if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
         float* pv = reinterpret_cast<float*>(cur);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) pv[e] = ex2(fmaf(pv[e], sc2, -mb2));
+        for (int e = 0; e < 32; ++e) {
+          const float y = fmaf(pv[e], sc2, -mb2);
+          pv[e] = ((e & 3) == 3) ? ex2_poly(y) : ex2(y);  // 3 MUFU : 1 polynomial
+        }
 #pragma unroll
         for (int e = 0; e < 32; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
         uint32_t pk[16];
@@ -1021,7 +1043,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
       configured_plain = true;
     }
     dim3 grid(a->S_q / 128, a->heads, a->BF);
-    attn_plain_kernel<<<grid, 320, kPlainSmem, stream>>>(p);
+    FZ_CUDA(launch_pdl(attn_plain_kernel, grid, dim3(320), kPlainSmem, stream, p));
     FZ_CUDA(cudaGetLastError());
     return FZ_OK;
   }
@@ -1051,7 +1073,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     configured = smem;
   }
   dim3 grid((a->S_q + 127) / 128, a->heads, a->BF);
-  attn_kernel<<<grid, 320, smem, stream>>>(p);
+  FZ_CUDA(launch_pdl(attn_kernel, grid, dim3(320), smem, stream, p));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }

@@ -41,6 +41,14 @@ void set_error(const char* fmt, ...);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// A UNet step is ~1170 short dependent launches; with programmatic stream serialisation the next kernel's CTAs are scheduled
+// while the current one drains and run their prologue (barrier init, TMEM allocation, descriptor prefetch) up to pdl_wait(),
+// which returns once the preceding kernel has completed and its writes are visible.  Every kernel launched through launch_pdl
+// calls pdl_launch_dependents() first and pdl_wait() before its first global-memory access (read OR write).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -273,6 +281,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
 }
 
 #endif  // __CUDACC__
+
+// Launch with programmatic stream serialisation (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // host: tensor-map encode through the driver entry point (no link-time libcuda dependency)

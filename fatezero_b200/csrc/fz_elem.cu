@@ -33,16 +33,26 @@ struct alignas(16) Half8 {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxSlots = 4;
+// 1 MiB workspace: [0, 768 KiB) per-CTA partial sums, then (sum, sumsq) per (image, group), then one arrival counter per image.
+// The counters must be zero before the first call (the Python layer allocates the workspace zeroed); every call leaves them zero.
+constexpr size_t kGnStatsOffset = 768 * 1024;
+constexpr size_t kGnCounterOffset = 960 * 1024;
 
 // Statistics pass: every CTA reduces its pixel chunk of one image to per-group partial (sum, sumsq) WITHOUT atomics
 // (v0 used ~4k contended shared-memory atomics per CTA): registers -> smem [TY][C] -> per channel -> per group -> partial[nb][chunk][g].
+// The chunks are large (about two CTAs per SM for the whole tensor) so that this reduction tail is amortised, and each thread keeps
+// kGnBatch independent 16-byte loads in flight.  The LAST CTA of an image folds the image's chunks into image_sums[nb][g]; the apply
+// kernel adds the frames_per_stat images of its statistics set (v2 had every apply CTA re-reduce all partials: ~150 KB of L2 reads).
+constexpr int kGnBatch = 8;
+
 template <int SLOTS>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, int TX,
-                                                             int px_per_cta, float2* __restrict__ partial) {
-  constexpr int slots = SLOTS;  // register arrays are sized by the template: 1 slot for C <= 2048 keeps occupancy (bytes in flight) high
+                                                             int px_per_cta, float2* __restrict__ partial,
+                                                             float2* __restrict__ image_sums, unsigned* __restrict__ counters) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float gn_smem[];  // [TY][C] sums, [TY][C] sumsq
   const int nb = blockIdx.y;
-  const int CV = C / 8;
   const int cpg = C / G;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = kGnThreads / TX;
@@ -57,18 +67,28 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
   const int p1 = min(HW, p0 + px_per_cta);
   if (ty < TY) {
     const __half* xb = x + (static_cast<long long>(nb) * HW) * C;
-#pragma unroll 4
-    for (int p = p0 + ty; p < p1; p += TY) {
+    constexpr int U = kGnBatch / SLOTS;
+    for (int p = p0 + ty; p < p1; p += TY * U) {
+      Half8 h[U][SLOTS];
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        const int cv = tx + s * TX;
-        if (s < slots) {
-          const Half8 h = *reinterpret_cast<const Half8*>(xb + static_cast<long long>(p) * C + cv * 8);
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * TY;
+        if (pp < p1) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float f = __half2float(h.v[e]);
-            acc[s][e] += f;
-            acc2[s][e] += f * f;
+          for (int s = 0; s < SLOTS; ++s) h[u][s] = *reinterpret_cast<const Half8*>(xb + static_cast<long long>(pp) * C + (tx + s * TX) * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p + u * TY < p1) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float f = __half2float(h[u][s].v[e]);
+              acc[s][e] += f;
+              acc2[s][e] = fmaf(f, f, acc2[s][e]);
+            }
           }
         }
       }
@@ -76,13 +96,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const int cv = tx + s * TX;
-      if (s < slots) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          s_sum[ty * C + cv * 8 + e] = acc[s][e];
-          s_sq[ty * C + cv * 8 + e] = acc2[s][e];
-        }
-      }
+      float4* d0 = reinterpret_cast<float4*>(s_sum + ty * C + cv * 8);
+      float4* d1 = reinterpret_cast<float4*>(s_sq + ty * C + cv * 8);
+      d0[0] = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+      d0[1] = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+      d1[0] = make_float4(acc2[s][0], acc2[s][1], acc2[s][2], acc2[s][3]);
+      d1[1] = make_float4(acc2[s][4], acc2[s][5], acc2[s][6], acc2[s][7]);
     }
   }
   __syncthreads();
@@ -97,48 +116,53 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
     float a = 0.f, b = 0.f;
     for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { a += s_sum[c]; b += s_sq[c]; }
     partial[(static_cast<long long>(nb) * gridDim.x + blockIdx.x) * G + threadIdx.x] = make_float2(a, b);
+    __threadfence();
   }
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&counters[nb], 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < G) {
+    double a = 0.0, b = 0.0;
+    const float2* pp = partial + static_cast<long long>(nb) * gridDim.x * G + threadIdx.x;
+    for (unsigned i = 0; i < gridDim.x; ++i) {
+      const float2 v = __ldcg(pp + static_cast<size_t>(i) * G);
+      a += v.x;
+      b += v.y;
+    }
+    image_sums[nb * G + threadIdx.x] = make_float2(static_cast<float>(a), static_cast<float>(b));
+  }
+  if (threadIdx.x == 0) counters[nb] = 0;  // ready for the next call (stream order)
 }
 
 template <int SLOTS>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, int C, int G,
-                                                             int frames_per_stat, int TX, int px_per_cta, int chunks,
-                                                             const float2* __restrict__ partial, const float* __restrict__ gamma,
+                                                             int frames_per_stat, int TX, int px_per_cta,
+                                                             const float2* __restrict__ image_sums, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int silu) {
-  constexpr int slots = SLOTS;
-  __shared__ double s_red[kGnThreads][2];
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
   const int nb = blockIdx.y;
-  const int CV = C / 8;
   const int cpg = C / G;
-  // group statistics of this image's stat set: sum the partials of its frames_per_stat images x chunks (fp64)
-  {
-    const int first_nb = (nb / frames_per_stat) * frames_per_stat;
-    const int n_part = frames_per_stat * chunks;  // partials per group, contiguous per image: [(nb*chunks + chunk)*G + g]
-    const int g = threadIdx.x % G, lane_j = threadIdx.x / G, n_j = kGnThreads / G;
-    double a = 0.0, b = 0.0;
-    if (lane_j < n_j) {
-      for (int i = lane_j; i < n_part; i += n_j) {
-        const float2 v = partial[(static_cast<long long>(first_nb) * chunks + i) * G + g];
-        a += v.x;
-        b += v.y;
-      }
+  if (threadIdx.x < G) {
+    const int first = (nb / frames_per_stat) * frames_per_stat;
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < frames_per_stat; ++i) {
+      const float2 v = image_sums[(first + i) * G + threadIdx.x];
+      sa += v.x;
+      sb += v.y;
     }
-    s_red[threadIdx.x][0] = a;
-    s_red[threadIdx.x][1] = b;
-    __syncthreads();
-    if (threadIdx.x < G) {
-      double sa = 0.0, sb = 0.0;
-      for (int j = 0; j < n_j; ++j) { sa += s_red[j * G + threadIdx.x][0]; sb += s_red[j * G + threadIdx.x][1]; }
-      const double cnt = static_cast<double>(cpg) * HW * frames_per_stat;
-      const double mean = sa / cnt;
-      double var = sb / cnt - mean * mean;
-      if (var < 0) var = 0;
-      s_mean[threadIdx.x] = static_cast<float>(mean);
-      s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
-    __syncthreads();
+    const double cnt = static_cast<double>(cpg) * HW * frames_per_stat;
+    const double mean = sa / cnt;
+    double var = sb / cnt - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
+  __syncthreads();
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int TY = kGnThreads / TX;
   if (ty >= TY) return;
@@ -146,49 +170,61 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int cv = tx + s * TX;
-    if (s < slots) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cv * 8 + e;
-        const int g = c / cpg;
-        sc[s][e] = s_rstd[g] * gamma[c];
-        sh[s][e] = beta[c] - s_mean[g] * s_rstd[g] * gamma[c];
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int g = (cv * 8 + e) / cpg;
+      sc[s][e] = s_rstd[g] * gg[e];
+      sh[s][e] = bb[e] - s_mean[g] * s_rstd[g] * gg[e];
     }
   }
   const int p0 = blockIdx.x * px_per_cta;
   const int p1 = min(HW, p0 + px_per_cta);
   const long long base = (static_cast<long long>(nb) * HW) * C;
-#pragma unroll 4
-  for (int p = p0 + ty; p < p1; p += TY) {
+  constexpr int U = (SLOTS == 1) ? 4 : (SLOTS == 2 ? 2 : 1);
+  for (int p = p0 + ty; p < p1; p += TY * U) {
+    Half8 h[U][SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int cv = tx + s * TX;
-      if (s < slots) {
-        const long long off = base + static_cast<long long>(p) * C + cv * 8;
-        const Half8 h = *reinterpret_cast<const Half8*>(x + off);
-        Half8 o;
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * TY;
+      if (pp < p1) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v = __half2float(h.v[e]) * sc[s][e] + sh[s][e];
-          if (silu) v = v / (1.0f + __expf(-v));
-          o.v[e] = __float2half_rn(v);
+        for (int s = 0; s < SLOTS; ++s) h[u][s] = *reinterpret_cast<const Half8*>(x + base + static_cast<long long>(pp) * C + (tx + s * TX) * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * TY;
+      if (pp < p1) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          Half8 o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = fmaf(__half2float(h[u][s].v[e]), sc[s][e], sh[s][e]);
+            if (silu) v = __fdividef(v, 1.0f + __expf(-v));  // fast reciprocal: the IEEE division made this kernel MUFU/issue-bound
+            o.v[e] = __float2half_rn(v);
+          }
+          *reinterpret_cast<Half8*>(y + base + static_cast<long long>(pp) * C + (tx + s * TX) * 8) = o;
         }
-        *reinterpret_cast<Half8*>(y + off) = o;
       }
     }
   }
 }
 
-static void gn_geometry(int C, int HW, int NB, int* TX, int* slots, int* px_per_cta, int* chunks) {
+// TX * slots == C / 8 exactly, slots in {1, 2, 4}; px_per_cta so that the whole tensor is covered by about `ctas_per_sm` CTAs per SM.
+static void gn_geometry(int C, int HW, int NB, int ctas_per_sm, int* TX, int* slots, int* px_per_cta, int* chunks) {
   const int CV = C / 8;
   int s = (CV + kGnThreads - 1) / kGnThreads;
-  while (CV % s || s == 3) ++s;  // TX * slots == CV exactly, slots in {1, 2, 4}
+  while (CV % s || s == 3) ++s;
   *slots = s;
   *TX = CV / s;
   const int TY = kGnThreads / *TX;
-  int want = std::max(1, ((s == 1 ? 8 : 4) * sm_count()) / std::max(1, NB));  // 1-slot kernels use ~40 registers: 8 CTAs per SM resident
-  int ppc = std::max(TY, (HW + want - 1) / want);
+  const int want = std::max(1, (ctas_per_sm * sm_count()) / std::max(1, NB));
+  const int ppc = std::max(TY, (HW + want - 1) / want);
   *px_per_cta = ppc;
   *chunks = (HW + ppc - 1) / ppc;
 }
@@ -204,6 +240,8 @@ template <int NV, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long M, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= M) return;
   const int CV = C / 8;
@@ -275,6 +313,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 // nearest 2x upsample (resnet.py:145) and channel concat (unet_3d_blocks.py:522,611), NHWC
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const Half8* __restrict__ x, Half8* __restrict__ y, int NB, int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(NB) * (2 * H) * (2 * W) * CV;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cv = i % CV;
@@ -288,6 +328,8 @@ __global__ void upsample2x_kernel(const Half8* __restrict__ x, Half8* __restrict
 }
 
 __global__ void concat2_kernel(const Half8* __restrict__ a, int CVa, const Half8* __restrict__ b, int CVb, Half8* __restrict__ y, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = CVa + CVb;
   const long long total = rows * CV;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -419,6 +461,8 @@ constexpr int kTaMaxF = 32;
 __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int F, int HW,
                                                            int heads, int d, float scale) {
   extern __shared__ __half ta_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int C = heads * d;
@@ -467,6 +511,114 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
       for (int g = 0; g < F; ++g) a += sp[f * F + g] * __half2float(sv[g * d + dd]);
       const long long row = (static_cast<long long>(b) * F + f) * HW + p;
       out[row * C + h * d + dd] = __float2half_rn(a);
+    }
+    __syncwarp();
+  }
+}
+
+// Pixel-major variant (the one the step uses: F <= 8): one warp owns (pixel, head group) with all F frames, where a head group is
+// hg consecutive heads (hg * d = 320 channels for the SD head sizes 40 / 80 / 160, so the warp's working set is always 15 KB).
+// The F q|k|v segments (3 x 640 contiguous bytes per frame) are fetched with coalesced 16-byte loads into shared memory (row
+// stride 3*gd + 8 halves, so the 8 lanes of a quarter-warp, one frame each, hit 8 distinct 16-byte bank groups); lane r handles the
+// query rows (head, frame) = (r / F, r % F), r + 32, ...: scores against the F keys of its head (shared-memory broadcast reads),
+// fp32 softmax, probabilities rounded to fp16 like the reference, PV, and the result replaces its own q slice; the warp then writes
+// the F output segments with coalesced 16-byte stores.  v1 (warp per (pixel, head), 4-byte loads, 80-byte segments) ran at 0.9 TB/s.
+template <int F>
+__global__ void __launch_bounds__(256) temporal_attn_px_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int HW, int heads,
+                                                              int d, int hg, float scale) {
+  extern __shared__ uint4 tap_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int C = heads * d;
+  const int gd = hg * d;          // channels of one head group
+  const int gv = gd / 8;          // 16-byte vectors per q / k / v segment
+  const int RS8 = 3 * gv + 1;     // shared-memory row stride in 16-byte units
+  const int groups = heads / hg;
+  uint4* sm = tap_smem + static_cast<size_t>(warp) * F * RS8;
+  const int rows = hg * F;
+  const long long items = static_cast<long long>(B) * HW * groups;
+  for (long long it = static_cast<long long>(blockIdx.x) * wpb + warp; it < items; it += static_cast<long long>(gridDim.x) * wpb) {
+    const int grp = it % groups;
+    const int p = (it / groups) % HW;
+    const int b = it / (static_cast<long long>(groups) * HW);
+    // ---- gather: F rows x 3 segments x gv vectors, 8 loads in flight per lane ----
+    const int total = F * 3 * gv;
+    for (int base = 0; base < total; base += 8 * 32) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * 32 + lane;
+        if (idx < total) {
+          const int f = idx / (3 * gv), c = idx - f * 3 * gv, part = c / gv, cc = c - part * gv;
+          v[u] = __ldg(reinterpret_cast<const uint4*>(qkv + ((static_cast<long long>(b) * F + f) * HW + p) * 3 * C + part * C + grp * gd) + cc);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * 32 + lane;
+        if (idx < total) {
+          const int f = idx / (3 * gv), c = idx - f * 3 * gv;
+          sm[f * RS8 + c] = v[u];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- per query row ----
+    for (int r = lane; r < rows; r += 32) {
+      const int h = r / F, f = r - h * F;
+      const uint4* qp = sm + f * RS8 + (h * d) / 8;
+      float sc[F];
+#pragma unroll
+      for (int g = 0; g < F; ++g) sc[g] = 0.f;
+      for (int j = 0; j < d / 8; ++j) {
+        const uint4 q8 = qp[j];
+        const __half2* qh = reinterpret_cast<const __half2*>(&q8);
+        const float2 q0 = __half22float2(qh[0]), q1 = __half22float2(qh[1]), q2 = __half22float2(qh[2]), q3 = __half22float2(qh[3]);
+#pragma unroll
+        for (int g = 0; g < F; ++g) {
+          const uint4 k8 = sm[g * RS8 + gv + (h * d) / 8 + j];
+          const __half2* kh = reinterpret_cast<const __half2*>(&k8);
+          const float2 k0 = __half22float2(kh[0]), k1 = __half22float2(kh[1]), k2 = __half22float2(kh[2]), k3 = __half22float2(kh[3]);
+          sc[g] += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y + q3.x * k3.x + q3.y * k3.y;
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < F; ++g) { sc[g] *= scale; mx = fmaxf(mx, sc[g]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < F; ++g) { sc[g] = __expf(sc[g] - mx); sum += sc[g]; }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int g = 0; g < F; ++g) sc[g] = __half2float(__float2half_rn(sc[g] * inv));
+      uint4* op = sm + f * RS8 + (h * d) / 8;  // own q slice: nobody else reads it
+      for (int j = 0; j < d / 8; ++j) {
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < F; ++g) {
+          const uint4 v8 = sm[g * RS8 + 2 * gv + (h * d) / 8 + j];
+          const __half2* vh = reinterpret_cast<const __half2*>(&v8);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 vv = __half22float2(vh[e]);
+            o[2 * e] = fmaf(sc[g], vv.x, o[2 * e]);
+            o[2 * e + 1] = fmaf(sc[g], vv.y, o[2 * e + 1]);
+          }
+        }
+        uint4 w;
+        __half2* wh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wh[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+        op[j] = w;
+      }
+    }
+    __syncwarp();
+    // ---- scatter: F rows x gv vectors ----
+    for (int idx = lane; idx < F * gv; idx += 32) {
+      const int f = idx / gv, c = idx - f * gv;
+      reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * F + f) * HW + p) * C + grp * gd)[c] = sm[f * RS8 + c];
     }
     __syncwarp();
   }
@@ -592,10 +744,11 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
   FZ_CHECK_ARG(x && y && gamma && beta && workspace_f64, "fz_groupnorm: null pointer");
   FZ_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64, "fz_groupnorm: C=%d groups=%d unsupported", C, groups);
   FZ_CHECK_ARG(frames_per_stat >= 1 && NB % frames_per_stat == 0, "fz_groupnorm: NB %% frames_per_stat != 0");
-  int TX, slots, ppc, chunks;
-  gn_geometry(C, HW, NB, &TX, &slots, &ppc, &chunks);
+  int TX, slots, ppc, chunks, ppc_apply, chunks_apply;
+  gn_geometry(C, HW, NB, 2, &TX, &slots, &ppc, &chunks);              // statistics: few fat CTAs (amortise the reduction tail)
+  gn_geometry(C, HW, NB, 4, &TX, &slots, &ppc_apply, &chunks_apply);  // apply: one full wave of 4 CTAs per SM
   FZ_CHECK_ARG(slots <= kGnMaxSlots, "fz_groupnorm: C=%d too large", C);
-  FZ_CHECK_ARG(static_cast<size_t>(NB) * chunks * groups * sizeof(float2) <= (1u << 20), "fz_groupnorm: workspace (1 MiB) too small");
+  FZ_CHECK_ARG(static_cast<size_t>(NB) * chunks * groups * sizeof(float2) <= kGnStatsOffset && NB <= 256, "fz_groupnorm: workspace (1 MiB) too small");
   const int TY = kGnThreads / TX;
   const size_t smem = static_cast<size_t>(2) * TY * C * sizeof(float);
   static size_t configured = 0;
@@ -605,15 +758,17 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
     FZ_CUDA(cudaFuncSetAttribute(gn_stats_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  dim3 grid(chunks, NB);
   float2* partial = static_cast<float2*>(workspace_f64);
+  float2* image_sums = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace_f64) + kGnStatsOffset);
+  unsigned* counters = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(workspace_f64) + kGnCounterOffset);
   const __half* xh = static_cast<const __half*>(x);
   __half* yh = static_cast<__half*>(y);
-#define FZ_GN_LAUNCH(SL)                                                                                                          \
-  do {                                                                                                                             \
-    gn_stats_kernel<SL><<<grid, kGnThreads, smem, stream>>>(xh, HW, C, groups, TX, ppc, partial);                                  \
-    gn_apply_kernel<SL><<<grid, kGnThreads, 0, stream>>>(xh, yh, HW, C, groups, frames_per_stat, TX, ppc, chunks, partial, gamma, \
-                                                         beta, eps, silu);                                                         \
+#define FZ_GN_LAUNCH(SL)                                                                                                             \
+  do {                                                                                                                                \
+    FZ_CUDA(launch_pdl(gn_stats_kernel<SL>, dim3(chunks, NB), dim3(kGnThreads), smem, stream, xh, HW, C, groups, TX, ppc, partial,      \
+                       image_sums, counters));                                                                                       \
+    FZ_CUDA(launch_pdl(gn_apply_kernel<SL>, dim3(chunks_apply, NB), dim3(kGnThreads), 0, stream, xh, yh, HW, C, groups,                 \
+                       frames_per_stat, TX, ppc_apply, static_cast<const float2*>(image_sums), gamma, beta, eps, silu));             \
   } while (0)
   if (slots == 1) FZ_GN_LAUNCH(1);
   else if (slots == 2) FZ_GN_LAUNCH(2);
@@ -631,7 +786,8 @@ extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, cons
   const __half* xh = static_cast<const __half*>(x);
   __half* yh = static_cast<__half*>(y);
 #define FZ_LN_LAUNCH(NV, ROWS) \
-  layernorm_kernel<NV, ROWS><<<static_cast<unsigned>((M + 8 * ROWS - 1) / (8 * ROWS)), 256, 0, stream>>>(xh, yh, M, C, gamma, beta, eps)
+  FZ_CUDA(launch_pdl(layernorm_kernel<NV, ROWS>, dim3(static_cast<unsigned>((M + 8 * ROWS - 1) / (8 * ROWS))), dim3(256), 0, stream, xh, yh, M, C, \
+                     gamma, beta, eps))
   switch (nv) {
     case 1: FZ_LN_LAUNCH(1, 4); break;
     case 2: FZ_LN_LAUNCH(2, 4); break;
@@ -650,7 +806,8 @@ extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, cons
 extern "C" int fz_upsample2x_nhwc_f16(const void* x, void* y, int NB, int H, int W, int C, cudaStream_t stream) {
   FZ_CHECK_ARG(x && y && C % 8 == 0, "fz_upsample2x: bad args");
   const long long total = static_cast<long long>(NB) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const Half8*>(x), static_cast<Half8*>(y), NB, H, W, C / 8);
+  FZ_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, static_cast<const Half8*>(x), static_cast<Half8*>(y), NB, H, W,
+                     C / 8));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
@@ -658,8 +815,8 @@ extern "C" int fz_upsample2x_nhwc_f16(const void* x, void* y, int NB, int H, int
 extern "C" int fz_concat_channels_f16(const void* a, int Ca, const void* b, int Cb, void* y, long long rows, cudaStream_t stream) {
   FZ_CHECK_ARG(a && b && y && Ca % 8 == 0 && Cb % 8 == 0, "fz_concat_channels: bad args");
   const long long total = rows * ((Ca + Cb) / 8);
-  concat2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const Half8*>(a), Ca / 8, static_cast<const Half8*>(b), Cb / 8,
-                                                           static_cast<Half8*>(y), rows);
+  FZ_CUDA(launch_pdl(concat2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, static_cast<const Half8*>(a), Ca / 8,
+                     static_cast<const Half8*>(b), Cb / 8, static_cast<Half8*>(y), rows));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
@@ -696,8 +853,37 @@ extern "C" int fz_timestep_sinusoid(float t, float* out, int C0, int flip_sin_to
   return FZ_OK;
 }
 
+template <int F>
+static int launch_temporal_px(const void* qkv, void* out, int B, int HW, int heads, int d, int hg, float scale, cudaStream_t stream) {
+  const int wpb = 4;
+  const size_t per_warp = static_cast<size_t>(F) * (3 * hg * d / 8 + 1) * 16;
+  const size_t smem = per_warp * wpb;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    FZ_CUDA(cudaFuncSetAttribute(temporal_attn_px_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const int ctas_per_sm = std::max(1, std::min(8, static_cast<int>((220 * 1024) / (smem + 1024))));
+  const long long items = static_cast<long long>(B) * HW * (heads / hg);
+  const int grid = static_cast<int>(std::min<long long>((items + wpb - 1) / wpb, static_cast<long long>(sm_count()) * ctas_per_sm));
+  FZ_CUDA(launch_pdl(temporal_attn_px_kernel<F>, dim3(grid), dim3(wpb * 32), smem, stream, static_cast<const __half*>(qkv), static_cast<__half*>(out), B, HW,
+                     heads, d, hg, scale));
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}
+
 extern "C" int fz_temporal_attn_f16(const void* qkv, void* out, int B, int F, int HW, int heads, int d, float scale, cudaStream_t stream) {
   FZ_CHECK_ARG(qkv && out && F <= kTaMaxF && d % 2 == 0, "fz_temporal_attn: F=%d d=%d unsupported", F, d);
+  if (d % 8 == 0 && d <= 320) {
+    int hg = std::max(1, std::min(heads, 320 / d));  // heads per warp: 15 KB of q|k|v per (pixel, head group)
+    while (heads % hg) --hg;
+    switch (F) {
+      case 8: return launch_temporal_px<8>(qkv, out, B, HW, heads, d, hg, scale, stream);
+      case 4: return launch_temporal_px<4>(qkv, out, B, HW, heads, d, hg, scale, stream);
+      case 2: return launch_temporal_px<2>(qkv, out, B, HW, heads, d, hg, scale, stream);
+      default: break;
+    }
+  }
   const int wpb = 8;
   const size_t per_warp = static_cast<size_t>(3 * F * d + F * F * 2) * sizeof(__half);
   const size_t smem = per_warp * wpb;
@@ -708,7 +894,8 @@ extern "C" int fz_temporal_attn_f16(const void* qkv, void* out, int B, int F, in
   }
   const long long items = static_cast<long long>(B) * HW * heads;
   const int grid = static_cast<int>(std::min<long long>((items + wpb - 1) / wpb, static_cast<long long>(sm_count()) * 4));
-  temporal_attn_kernel<<<grid, wpb * 32, smem, stream>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, F, HW, heads, d, scale);
+  FZ_CUDA(launch_pdl(temporal_attn_kernel, dim3(grid), dim3(wpb * 32), smem, stream, static_cast<const __half*>(qkv), static_cast<__half*>(out), B, F, HW,
+                     heads, d, scale));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }

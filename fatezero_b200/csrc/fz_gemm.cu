@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.num_taps * p.k_blocks;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands / outputs are touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -508,7 +510,7 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  tapgemm_kernel<BN><<<grid, 320, Cfg::kSmemBytes, stream>>>(p);
+  FZ_CUDA(launch_pdl(tapgemm_kernel<BN>, dim3(grid), dim3(320), Cfg::kSmemBytes, stream, p));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }

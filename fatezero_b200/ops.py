@@ -126,7 +126,7 @@ _gn_ws = {}
 def _workspace(device, nbytes: int) -> torch.Tensor:
     ws = _gn_ws.get(device)
     if ws is None or ws.numel() * 8 < nbytes:
-        ws = torch.empty(max(nbytes // 8 + 1, 4096), dtype=torch.float64, device=device)
+        ws = torch.zeros(max(nbytes // 8 + 1, 4096), dtype=torch.float64, device=device)  # arrival counters start at zero
         _gn_ws[device] = ws
     return ws
 

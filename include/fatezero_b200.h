@@ -104,7 +104,8 @@ int fz_attention_f16(const fz_attn_args_t* args, fz_stream_t stream);
  * HBM-bound kernels of the step
  * --------------------------------------------------------------------------------------------------------- */
 /* GroupNorm (+SiLU) on NHWC fp16. frames_per_stat = F reproduces nn.GroupNorm on the 5-D tensor (resnet.py:338,369;
- * unet_3d_condition.py:439); 1 = per-frame (models/attention.py:112). workspace_f64: 1 MiB scratch for the per-chunk partial sums. */
+ * unet_3d_condition.py:439); 1 = per-frame (models/attention.py:112). workspace_f64: 1 MiB scratch (per-chunk partial sums, per-set statistics, arrival counters); it must be
+ * zero-filled once before the first call and is left consistent by every call (calls sharing it must be stream-ordered). */
 int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, const float* gamma,
                           const float* beta, float eps, int silu, void* workspace_f64, fz_stream_t stream);
 /* nn.LayerNorm over channels of token rows (models/attention.py:281,303,320,331) */

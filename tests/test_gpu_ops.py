@@ -203,7 +203,8 @@ def test_time_embedding(report):
     close(y2, rnd(640, 1280, scale=1280 ** -0.5, seed=2).half().float() @ F.silu(y), report, "rowvec_silu", atol=2e-3, rtol=1e-3)
 
 
-@pytest.mark.parametrize("B,Fr,HW,heads,d", [(2, 8, 64, 8, 40), (1, 3, 256, 4, 16), (1, 8, 16, 8, 160)])
+@pytest.mark.parametrize("B,Fr,HW,heads,d", [(2, 8, 64, 8, 40), (1, 3, 256, 4, 16), (1, 8, 16, 8, 160), (2, 8, 1024, 8, 80), (1, 4, 64, 8, 40),
+                                             (1, 2, 96, 4, 16)])
 def test_temporal_attn(B, Fr, HW, heads, d, report):
     C_ = heads * d
     qkv = rnd(B * Fr * HW, 3 * C_).half()
