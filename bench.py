@@ -113,8 +113,12 @@ def edit_clip(pipe, x0_dev, emb_src):
     """One full clip edit through the reference-facing API: inversion with STORE, then edit_type='swap'. Returns final latents."""
     from fatezero_b200 import controllers
     pipe.scheduler.set_timesteps(DDIM_STEPS)
+    old = getattr(pipe, "store_controller", None)
     pipe.store_controller = controllers.AttentionStore()
-    controllers.register_attention_control(pipe, pipe.store_controller)
+    controllers.register_attention_control(pipe, pipe.store_controller)  # also drops the previous clip's edit controller
+    if old is not None:
+        old.reset()  # the previous clip's 36 GiB map cache goes back to the caching allocator BEFORE this clip allocates its own
+    del old
     pipe.store_controller.LOW_RESOURCE = True
     inv = pipe.ddim_clean2noisy_loop(x0_dev, emb_src, pipe.store_controller)
     pipe.store_controller.LOW_RESOURCE = False

@@ -34,6 +34,10 @@ struct TapGemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmC;    // output [M, N] as (cols, rows), box {32 cols, 32 rows}, SWIZZLE_64B (epilogue TMA stores)
+  CUtensorMap tmR[2]; // skip tensors [M, N] folded into the accumulator as extra k-blocks: box {64 cols, 128 rows}
+  CUtensorMap tmE;    // identity blocks E[j][n][k] = (n == 64 j + k): (k : 64, n : 256, j : 4), box {64, BLOCK_N, 1}
+  int n_res;          // number of folded skip tensors (0..2); the epilogue then sees residual == residual2 == null
+  int res_kblocks;    // ceil(BLOCK_N / 64) extra k-blocks per folded skip tensor
   int use_tma_store;  // 0 = direct 16-byte stores (fallback for odd geometries)
   int a_rank;         // 2..5
   int M, N;           // valid output rows / columns (for GEGLU: N = number of OUTPUT columns = half the GEMM columns)
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int k_iters = p.num_taps * p.k_blocks;
+  const int k_iters = p.num_taps * p.k_blocks + p.n_res * p.res_kblocks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -156,6 +160,21 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               default: tma_load_5d(sa, &p.tmA, &full[stage], c0, c1, c2, c3, c4); break;
             }
             tma_load_3d(sb, &p.tmB, &full[stage], kb * kBlockK, n0, tap);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        // Skip connections ride the same pipeline as extra k-blocks: D += R[:, n0 + 64 j ...] * E_j^T with E_j a 0/1 selection block
+        // (exact: fp16 x 1.0 accumulated in fp32 after the last tap, the same order as an epilogue add).  The epilogue of a
+        // K = 320 linear used to wait ~1 us of exposed global-load latency per 32-column chunk for the skip tensor
+        // (65536 x 320 x 320 + skip: 40 us against 21 us without); here the loads are prefetched by the TMA ring like any operand.
+        for (int r = 0; r < p.n_res; ++r) {
+          for (int j = 0; j < p.res_kblocks; ++j) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kATileBytes;
+            mbar_expect_tx(&full[stage], kATileBytes + Cfg::kBTileBytes);
+            tma_load_2d(sa, &p.tmR[r], &full[stage], n0 + j * kBlockK, mt * p.rows_per_tile);
+            tma_load_3d(sb, &p.tmE, &full[stage], 0, 0, j);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -533,6 +552,51 @@ static int pick_block_n(int gemm_cols, int mode, int forced, int m_tiles) {
   return best;
 }
 
+// Selection blocks for folding skip tensors into the MMA pipeline: E[j][n][k] = 1 if n == 64 j + k (static device memory, filled once).
+__device__ __half g_eye[4][256][64];
+__global__ void eye_init_kernel() {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * 256 * 64; i += gridDim.x * blockDim.x) {
+    const int k = i % 64, n = (i / 64) % 256, j = i / (64 * 256);
+    (&g_eye[0][0][0])[i] = __float2half_rn(n == 64 * j + k ? 1.f : 0.f);
+  }
+}
+
+static int fold_residuals(TapGemmParams& p, int bn, cudaStream_t stream) {
+  p.n_res = 0;
+  p.res_kblocks = 0;
+  if (p.mode != FZ_EPI_ROWMAJOR || p.vt_col_start != INT_MAX || (!p.residual && !p.residual2)) return FZ_OK;
+  const __half* rs[2] = {p.residual, p.residual2};
+  const long long lds[2] = {p.ldr, p.ldr2};
+  for (int i = 0; i < 2; ++i)
+    if (rs[i] && ((reinterpret_cast<uintptr_t>(rs[i]) & 15) != 0 || lds[i] % 8 != 0)) return FZ_OK;  // not TMA-addressable: epilogue path
+  static __half* eye = nullptr;
+  if (!eye) {
+    FZ_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&eye), g_eye));
+    eye_init_kernel<<<64, 256, 0, stream>>>();
+    FZ_CUDA(cudaGetLastError());
+    // the table is read by TMA of kernels on ANY stream afterwards: make the one-time fill visible before returning
+    FZ_CUDA(cudaStreamSynchronize(stream));
+  }
+  {
+    uint64_t dims[3] = {64, 256, 4};
+    uint64_t strides[2] = {64, 64 * 256};
+    uint32_t box[3] = {64, static_cast<uint32_t>(bn), 1};
+    if (int rc = encode_tmap_f16(&p.tmE, eye, 3, dims, strides, box, true)) return rc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!rs[i]) continue;
+    uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lds[i])};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (int rc = encode_tmap_f16(&p.tmR[p.n_res], rs[i], 2, dims, strides, box, true)) return rc;
+    ++p.n_res;
+  }
+  p.res_kblocks = (bn + kBlockK - 1) / kBlockK;
+  p.residual = nullptr;
+  p.residual2 = nullptr;
+  return FZ_OK;
+}
+
 static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cudaStream_t stream) {
   // output tensor map for the TMA-store epilogue ([M, N_out] row-major, row stride ldo)
   p.use_tma_store = 0;
@@ -546,6 +610,7 @@ static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cuda
   }
   const int bn = pick_block_n(gemm_cols, p.mode, forced_bn, p.m_tiles);
   p.n_tiles = (gemm_cols + bn - 1) / bn;
+  if (int rc = fold_residuals(p, bn, stream)) return rc;
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);
     case 160: return launch_tapgemm<160>(p, stream);
