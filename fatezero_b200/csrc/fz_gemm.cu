@@ -79,16 +79,31 @@ struct TapGemmCfg {
 // exact-erf GELU (F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output rounding):
 // 1 MUFU.RCP + 1 MUFU.EX2 + 8 FMA instead of the ~40-instruction erff() — the GEGLU epilogue was XU/ALU-bound (ncu: 24 % tensor pipe).
 __device__ __forceinline__ float gelu_erf(float x) {
+  // single-instruction MUFU forms: __frcp_rn / exp2f expand to IEEE-exact sequences (~10 extra instructions each) and made the GEGLU
+  // epilogue latency-bound (measured 4900 cycles per 32x32 chunk, 84 % of the epilogue warp's time)
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+
+// Optional in-kernel cycle accounting (compile with -DFZ_GEMM_PROFILE, read with fz_debug_gemm_counters): CTA 0 only.
+//  [0] epilogue warp 2: loop total  [1] wait tfull  [2] TMEM load  [3] math  [4] wait for a free staging slot  [5] stage + TMA store
+//  [6] chunks  [7] tiles   [8] MMA thread: total  [9] wait tempty  [10] wait full   [12] producer: total  [13] wait empty
+__device__ long long g_gemm_dbg[16];
+#ifdef FZ_GEMM_PROFILE
+#define GP_NOW() clock64()
+#define GP_ADD(slot, expr) do { if (gp_on) gp[slot] += (expr); } while (0)
+#else
+#define GP_NOW() 0LL
+#define GP_ADD(slot, expr) do { } while (0)
+#endif
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
@@ -105,6 +120,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   pdl_launch_dependents();
+#ifdef FZ_GEMM_PROFILE
+  const bool gp_on = blockIdx.x == 0;
+  long long gp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.num_taps * p.k_blocks + p.n_res * p.res_kblocks;
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const long long gp_t0 = GP_NOW();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         int rem = mt * p.rows_per_tile;
@@ -148,7 +168,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           const int c1 = base[1] + p.tap_off[tap][1], c2 = base[2] + p.tap_off[tap][2];
           const int c3 = base[3] + p.tap_off[tap][3], c4 = base[4] + p.tap_off[tap][4];
           for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const long long gp_a = GP_NOW();
             mbar_wait(&empty[stage], phase ^ 1);
+            GP_ADD(13, GP_NOW() - gp_a);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kATileBytes;
             mbar_expect_tx(&full[stage], p.a_box_bytes + Cfg::kBTileBytes);
@@ -179,6 +201,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           }
         }
       }
+#ifdef FZ_GEMM_PROFILE
+      if (gp_on) { g_gemm_dbg[12] = GP_NOW() - gp_t0; g_gemm_dbg[13] = gp[13]; }
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -189,14 +214,19 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      const long long gp_m0 = GP_NOW();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
+        const long long gp_a = GP_NOW();
         mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        GP_ADD(9, GP_NOW() - gp_a);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
         for (int it = 0; it < k_iters; ++it) {
+          const long long gp_b = GP_NOW();
           mbar_wait(&full[stage], phase);
+          GP_ADD(10, GP_NOW() - gp_b);
           tc_fence_after();
           const uint32_t a_lo = smem_lo0 + stage * (Cfg::kStageBytes >> 4);
           const uint32_t b_lo = a_lo + (kATileBytes >> 4);
@@ -209,6 +239,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         }
         umma_commit(&tfull[buf]);
       }
+#ifdef FZ_GEMM_PROFILE
+      if (gp_on) { g_gemm_dbg[8] = GP_NOW() - gp_m0; g_gemm_dbg[9] = gp[9]; g_gemm_dbg[10] = gp[10]; }
+#endif
     }
   } else {
     // ===================== epilogue warps =====================
@@ -226,6 +259,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     auto store_chunk32 = [&](const uint4 (&o)[4], long long m_row, int col, int m_warp0, uint8_t* acquired) {
       if (p.use_tma_store) {
         uint8_t* slot = acquired;
+        const long long gp_a = GP_NOW();
         if (slot == nullptr) {
           slot = my_epi + (epi_count & 1) * 2048;
           if (epi_count >= 2) {
@@ -233,6 +267,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             __syncwarp();
           }
         }
+        const long long gp_b = GP_NOW();
+        GP_ADD(4, gp_b - gp_a);
         uint8_t* rowp = slot + lane * 64;
         const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -244,6 +280,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           tma_store_commit();
         }
         ++epi_count;
+        GP_ADD(5, GP_NOW() - gp_b);
+        GP_ADD(6, 1);
       } else {
         uint4* op = reinterpret_cast<uint4*>(p.out + m_row * p.ldo + col);
 #pragma unroll
@@ -285,13 +323,17 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       return my_epi + (epi_count & 1) * 2048;
     };
     int local = 0;
+    const long long gp_e0 = GP_NOW();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const long long m = static_cast<long long>(mt) * p.rows_per_tile + row_in_tile;
       const bool row_ok = row_in_tile < p.rows_per_tile && m < p.M;
+      const long long gp_w = GP_NOW();
       mbar_wait(&tfull[buf], use & 1);
+      GP_ADD(1, GP_NOW() - gp_w);
+      GP_ADD(7, 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BLOCK_N;
       if (p.mode == FZ_EPI_GEGLU) {
@@ -301,6 +343,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll 1
           for (int c = half * CH; c < HALF; c += 2 * CH) {
             uint32_t xa[CH], ga[CH];
+            const long long gp_l = GP_NOW();
             if constexpr (CH == 32) {
               tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(xa));
               tmem_ld_32x32b_x32(t_row + HALF + c, reinterpret_cast<uint32_t(&)[32]>(ga));
@@ -309,6 +352,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               tmem_ld_32x32b_x16(t_row + HALF + c, reinterpret_cast<uint32_t(&)[16]>(ga));
             }
             tmem_ld_wait();
+            const long long gp_c = GP_NOW();
+            GP_ADD(2, gp_c - gp_l);
             const int ocol0 = nt * HALF + c;
             const int m_warp0 = mt * p.rows_per_tile + quad * 32;
             const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
@@ -336,6 +381,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                 o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
                 o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
               }
+              GP_ADD(3, GP_NOW() - gp_c);
               if constexpr (CH == 32) {
                 store_chunk32(o, m, ocol0, m_warp0, nullptr);
               } else {
@@ -364,10 +410,21 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll 1
         for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
           uint32_t acc[CH];
+          const long long gp_l = GP_NOW();
+          const int col0 = nt * BLOCK_N + c;
+          // the bias row of this chunk is fetched BEFORE the TMEM load so that its global-load latency overlaps it
+          float4 bvec[CH / 4];
+          const bool bias_pre = p.bias != nullptr && col0 + CH <= p.N;
+          if (bias_pre) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) bvec[j] = __ldg(bp + j);
+          }
           if constexpr (CH == 32) tmem_ld_32x32b_x32(t_row + c, reinterpret_cast<uint32_t(&)[32]>(acc));
           else tmem_ld_32x32b_x16(t_row + c, reinterpret_cast<uint32_t(&)[16]>(acc));
           tmem_ld_wait();
-          const int col0 = nt * BLOCK_N + c;
+          const long long gp_c = GP_NOW();
+          GP_ADD(2, gp_c - gp_l);
           const int m_warp0 = mt * p.rows_per_tile + quad * 32;
           const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
           if (!warp_ok || col0 >= p.N) continue;
@@ -377,11 +434,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             float v[CH];
 #pragma unroll
             for (int e = 0; e < CH; ++e) v[e] = __uint_as_float(acc[e]);
-            if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+            if (bias_pre) {
 #pragma unroll
               for (int j = 0; j < CH / 4; ++j) {
-                const float4 b = __ldg(bp + j);
+                const float4 b = bvec[j];
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
@@ -443,6 +499,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
               o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
             }
+            GP_ADD(3, GP_NOW() - gp_c);
             if constexpr (CH == 32) {
               store_chunk32(o, m, col0, m_warp0, slot);
             } else {
@@ -496,6 +553,12 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
     if (p.use_tma_store && lane == 0) tma_store_wait_all<0>();
+#ifdef FZ_GEMM_PROFILE
+    if (gp_on && warp == 2 && lane == 0) {
+      g_gemm_dbg[0] = GP_NOW() - gp_e0;
+      for (int i = 1; i < 8; ++i) g_gemm_dbg[i] = gp[i];
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -646,6 +709,14 @@ static int fill_epilogue(TapGemmParams& p, const fz_epilogue_t* e, int M, int ge
 }  // namespace fz
 
 using namespace fz;
+
+// Development aid (not part of include/fatezero_b200.h): cycle counters of the last tap-GEMM launch, zeros unless built with
+// -DFZ_GEMM_PROFILE (tools/profile_gemm_epilogue.py).
+extern "C" int fz_debug_gemm_counters(long long* host16) {
+  FZ_CUDA(cudaDeviceSynchronize());
+  FZ_CUDA(cudaMemcpyFromSymbol(host16, g_gemm_dbg, sizeof(long long) * 16));
+  return FZ_OK;
+}
 
 // D[M,N] = A[M,K] * W[N,K]^T (+epilogue).  A, W fp16 row-major (lda, ldw in elements, multiples of 8).
 extern "C" int fz_gemm_f16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const fz_epilogue_t* epi,
