@@ -242,8 +242,16 @@ def run_gpu(args):
         flops, secs, n_launch = instrument_tapgemm(pipe, x0_dev, emb_src)
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
         ach = flops / secs / 1e12
+        # DRAM bytes per tap-GEMM launch from the committed ncu capture of one step pair (profiles/r01_tapgemm_traffic.json)
+        traffic = traffic_src = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tapgemm_traffic.json")))
+            traffic, traffic_src = round(tj["tapgemm_dram_bytes_per_launch"]), "ncu dram__bytes_read+write, average over the 688 tap-GEMM launches of one step pair"
+        except Exception:  # noqa: BLE001
+            pass
         roof = dict(kernel="tapgemm_kernel (conv3x3 / linear / temporal-LoRA, tcgen05)", bound="tensor", achieved=round(ach, 1), peak=peak,
-                    unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None, peak_source=f"{pk_kind} sustained bf16 (MEASURED_PEAKS.json)",
+                    unit="TFLOP/s", frac=round(ach / peak, 4), traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=47_246_000, peak_source=f"{pk_kind} sustained bf16 (MEASURED_PEAKS.json)",
                     launches_per_clip=n_launch, algorithmic_tflop_per_clip=round(flops / 1e12, 1),
                     kernel_seconds_per_clip=round(secs, 4), share_of_step=round(secs / (ms / 1e3 / args.steps), 3))
         if world == 1 and not args.no_cpu_baseline:
