@@ -245,41 +245,50 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= M) return;
   const int CV = C / 8;
-  Half8 buf[ROWS][NV];
-  float sum[ROWS], sq[ROWS];
+  // the rows are converted to fp32 ONCE and stay in registers for the mean, the centred second moment and the output
+  // (the kernel was issue-bound: 65 % issue slots busy, three half->float conversions per element)
+  Half8 raw[ROWS][NV];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    sum[r] = 0.f;
     const long long row = min(row0 + r, M - 1);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int cv = lane + i * 32;
-      if (cv < CV) buf[r][i] = *reinterpret_cast<const Half8*>(x + row * C + cv * 8);
+      if (cv < CV) raw[r][i] = *reinterpret_cast<const Half8*>(x + row * C + cv * 8);
     }
   }
+  float v[ROWS][NV][8];
+  float sum[ROWS], sq[ROWS];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
+    sum[r] = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (lane + i * 32 < CV) {
+      const bool ok = lane + i * 32 < CV;
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw[r][i]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sum[r] += __half2float(buf[r][i].v[e]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = ok ? __half22float2(h2[e]) : make_float2(0.f, 0.f);
+        v[r][i][2 * e] = f.x;
+        v[r][i][2 * e + 1] = f.y;
+        sum[r] += f.x + f.y;
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
   }
+  const float inv_c = 1.0f / C;
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    const float mean = sum[r] / C;
+    const float mean = sum[r] * inv_c;
     sq[r] = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (lane + i * 32 < CV) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float d = __half2float(buf[r][i].v[e]) - mean;
-          sq[r] += d * d;
+          const float d = v[r][i][e] - mean;
+          sq[r] = fmaf(d, d, sq[r]);
         }
       }
     }
@@ -287,23 +296,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     for (int o = 16; o > 0; o >>= 1) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
   }
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const long long row = row0 + r;
-    if (row >= M) break;
-    const float mean = sum[r] / C;
-    const float rstd = rsqrtf(sq[r] / C + eps);
+  for (int i = 0; i < NV; ++i) {
+    const int cv = lane + i * 32;
+    if (cv < CV) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int cv = lane + i * 32;
-      if (cv < CV) {
-        Half8 o;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int r = 0; r < ROWS; ++r) {
+        const long long row = row0 + r;
+        if (row < M) {
+          const float rstd = rsqrtf(sq[r] * inv_c + eps);
+          const float shift = -sum[r] * inv_c * rstd;  // (x - mean) * rstd == x * rstd + shift
+          Half8 o;
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o.v[e] = __float2half_rn((__half2float(buf[r][i].v[e]) - mean) * rstd * gg[e] + bb[e]);
-        *reinterpret_cast<Half8*>(y + row * C + cv * 8) = o;
+          for (int e = 0; e < 4; ++e)
+            o2[e] = __floats2half2_rn(fmaf(fmaf(v[r][i][2 * e], rstd, shift), gg[2 * e], bb[2 * e]),
+                                      fmaf(fmaf(v[r][i][2 * e + 1], rstd, shift), gg[2 * e + 1], bb[2 * e + 1]));
+          *reinterpret_cast<Half8*>(y + row * C + cv * 8) = o;
+        }
       }
     }
   }
@@ -790,11 +803,11 @@ extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, cons
                      gamma, beta, eps))
   switch (nv) {
     case 1: FZ_LN_LAUNCH(1, 4); break;
-    case 2: FZ_LN_LAUNCH(2, 4); break;
+    case 2: FZ_LN_LAUNCH(2, 2); break;
     case 3: FZ_LN_LAUNCH(3, 2); break;
-    case 4: FZ_LN_LAUNCH(4, 2); break;
-    case 5: FZ_LN_LAUNCH(5, 2); break;
-    case 6: FZ_LN_LAUNCH(6, 2); break;
+    case 4: FZ_LN_LAUNCH(4, 1); break;
+    case 5: FZ_LN_LAUNCH(5, 1); break;
+    case 6: FZ_LN_LAUNCH(6, 1); break;
     case 7: FZ_LN_LAUNCH(7, 1); break;
     default: FZ_LN_LAUNCH(8, 1); break;
   }

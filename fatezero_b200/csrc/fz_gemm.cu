@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               float xv[CH], gv[CH];
 #pragma unroll
               for (int e = 0; e < CH; ++e) { xv[e] = __uint_as_float(xa[e]); gv[e] = __uint_as_float(ga[e]); }
+              // (prefetching these 64 bias values before the TMEM load was measured: the extra live registers spill under the
+              //  168-register cap of a 10-warp CTA and the epilogue gets 1.6x slower)
               if (p.bias) {
                 const float4* bx = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c);
                 const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + HALF + c);
