@@ -93,14 +93,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
-def build_pipe(device):
+def build_pipe(device, degenerate_temporal: bool = False):
     from fatezero_b200 import DDIMScheduler, P2pDDIMSpatioTemporalPipeline, UNetPseudo3DConditionModel, synth
     from fatezero_b200.unet import unet_param_spec
     cfg = synth.SD14_UNET_CONFIG
     unet = UNetPseudo3DConditionModel(**cfg, **MODEL_CONFIG)
     spec = unet_param_spec(dict(cfg), MODEL_CONFIG)
     # non-degenerate temporal weights: nothing on the path is an identity that could be skipped
-    unet.load_state_dict(synth.synth_state_dict({k: v[0] for k, v in spec.items()}, seed=0, degenerate_temporal=False))
+    unet.load_state_dict(synth.synth_state_dict({k: v[0] for k, v in spec.items()}, seed=0, degenerate_temporal=degenerate_temporal))
     unet.to(device)
     te = synth.ToyTextEncoder(cfg["cross_attention_dim"]).to(device)
     pipe = P2pDDIMSpatioTemporalPipeline(synth.VaeStub(), te, synth.ToyTokenizer(), unet, DDIMScheduler())
@@ -188,8 +188,17 @@ def run_gpu(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    pipe = build_pipe(device)
-    x0_host = (synth.synth_latents(FRAMES, SIZE, SIZE, seed=1 + rank) * 0.5).pin_memory()
+    shard_frames = args.shard == "frames" and world > 1
+    # --shard frames: ONE clip, its frames split over the ranks (K/V all-gather + GroupNorm-statistics all-reduce);
+    # needs identity temporal layers, i.e. the un-tuned SD weights of the reference's zero-shot configs (from_2d_model).
+    pipe = build_pipe(device, degenerate_temporal=shard_frames)
+    if shard_frames:
+        from fatezero_b200 import dist as fzdist
+        pipe.unet.set_frame_shard(rank, world)
+        x_full = synth.synth_latents(FRAMES, SIZE, SIZE, seed=1) * 0.5
+        x0_host = fzdist.frame_slice(x_full, rank, world).pin_memory()
+    else:
+        x0_host = (synth.synth_latents(FRAMES, SIZE, SIZE, seed=1 + rank) * 0.5).pin_memory()
     out_host = torch.empty_like(x0_host).pin_memory()
     x0_dev = x0_host.to(device)
     emb_src = pipe._encode_prompt(SRC, device, 1, True, None)
@@ -233,11 +242,13 @@ def run_gpu(args):
     launches = _lib.kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
-    frames_total = FRAMES * world * args.steps
+    frames_total = FRAMES * (1 if shard_frames else world) * args.steps
     value = frames_total / (ms / 1e3)
     e2e_value = frames_total / (ms_e2e / 1e3)
     pk, pk_kind = peaks()
     roof = cpu = None
+    if shard_frames and rank != 0:
+        instrument_tapgemm(pipe, x0_dev, emb_src)  # the sharded forward is collective: every rank has to run the instrumented clip
     if rank == 0:
         flops, secs, n_launch = instrument_tapgemm(pipe, x0_dev, emb_src)
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
@@ -259,9 +270,13 @@ def run_gpu(args):
     if rank == 0:
         line = dict(metric="edited frames/sec (512x512x8f, 50 DDIM steps: inversion + attention-fused edit)", value=round(value, 4),
                     unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 2),
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 (fp32 accumulate)", data="synthetic",
-                    config=dict(workload=WORKLOAD, frames=FRAMES, latent=f"{SIZE}x{SIZE}", ddim_steps=DDIM_STEPS,
-                                model_config=MODEL_CONFIG, parallelism=("single GPU" if world == 1 else f"{world} independent clips (replicas)"),
+                    higher_is_better=True, scaling=("strong" if shard_frames else "weak"), vs_baseline=None, dtype="f16 (fp32 accumulate)",
+                    data="synthetic",
+                    config=dict(workload=WORKLOAD + (" [identity temporal layers: un-tuned SD weights]" if shard_frames else ""), frames=FRAMES,
+                                latent=f"{SIZE}x{SIZE}", ddim_steps=DDIM_STEPS, model_config=MODEL_CONFIG,
+                                parallelism=("single GPU" if world == 1 else
+                                             (f"frames of one clip over {world} GPUs (NCCL K/V all-gather + GroupNorm all-reduce)" if shard_frames
+                                              else f"{world} independent clips (replicas)")),
                                 l2="working set (36 GiB map cache + activations) far exceeds the 126 MB L2; no explicit flush"),
                     clocks=clocks, e2e=dict(value=round(e2e_value, 4), unit="frames/s", h2d_bytes_per_step=x0_host.numel() * 4,
                                             d2h_bytes_per_step=out_host.numel() * 4),
@@ -349,6 +364,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="clips", choices=["clips", "frames"],
+                    help="N > 1: independent clips per rank (default, weak scaling) or the frames of ONE clip over the ranks (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

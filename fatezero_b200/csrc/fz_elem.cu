@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __half* __re
 
 template <int SLOTS>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, int HW, int C, int G,
-                                                             int frames_per_stat, int TX, int px_per_cta,
+                                                             int frames_per_stat, int count_frames, int TX, int px_per_cta,
                                                              const float2* __restrict__ image_sums, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int silu) {
   pdl_launch_dependents();
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
       sa += v.x;
       sb += v.y;
     }
-    const double cnt = static_cast<double>(cpg) * HW * frames_per_stat;
+    const double cnt = static_cast<double>(cpg) * HW * count_frames;  // count_frames > frames_per_stat: frames held by other GPUs
     const double mean = sa / cnt;
     double var = sb / cnt - mean * mean;
     if (var < 0) var = 0;
@@ -752,9 +752,10 @@ static inline int grid_for(long long total, int threads) {
 
 using namespace fz;
 
-extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, const float* gamma,
-                                     const float* beta, float eps, int silu, void* workspace_f64, cudaStream_t stream) {
-  FZ_CHECK_ARG(x && y && gamma && beta && workspace_f64, "fz_groupnorm: null pointer");
+// which = 1: statistics only, 2: apply only (image_sums supplied by the caller), 3: both
+static int groupnorm_impl(int which, const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, int count_frames,
+                          const float* gamma, const float* beta, float eps, int silu, void* workspace_f64, const void* sums_in,
+                          cudaStream_t stream) {
   FZ_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64, "fz_groupnorm: C=%d groups=%d unsupported", C, groups);
   FZ_CHECK_ARG(frames_per_stat >= 1 && NB % frames_per_stat == 0, "fz_groupnorm: NB %% frames_per_stat != 0");
   int TX, slots, ppc, chunks, ppc_apply, chunks_apply;
@@ -772,16 +773,19 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
     configured = smem;
   }
   float2* partial = static_cast<float2*>(workspace_f64);
-  float2* image_sums = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace_f64) + kGnStatsOffset);
-  unsigned* counters = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(workspace_f64) + kGnCounterOffset);
+  float2* image_sums = workspace_f64 ? reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace_f64) + kGnStatsOffset) : nullptr;
+  unsigned* counters = workspace_f64 ? reinterpret_cast<unsigned*>(static_cast<uint8_t*>(workspace_f64) + kGnCounterOffset) : nullptr;
+  const float2* sums = sums_in ? static_cast<const float2*>(sums_in) : image_sums;
   const __half* xh = static_cast<const __half*>(x);
   __half* yh = static_cast<__half*>(y);
 #define FZ_GN_LAUNCH(SL)                                                                                                             \
   do {                                                                                                                                \
-    FZ_CUDA(launch_pdl(gn_stats_kernel<SL>, dim3(chunks, NB), dim3(kGnThreads), smem, stream, xh, HW, C, groups, TX, ppc, partial,      \
-                       image_sums, counters));                                                                                       \
-    FZ_CUDA(launch_pdl(gn_apply_kernel<SL>, dim3(chunks_apply, NB), dim3(kGnThreads), 0, stream, xh, yh, HW, C, groups,                 \
-                       frames_per_stat, TX, ppc_apply, static_cast<const float2*>(image_sums), gamma, beta, eps, silu));             \
+    if (which & 1)                                                                                                                    \
+      FZ_CUDA(launch_pdl(gn_stats_kernel<SL>, dim3(chunks, NB), dim3(kGnThreads), smem, stream, xh, HW, C, groups, TX, ppc, partial,    \
+                         image_sums, counters));                                                                                     \
+    if (which & 2)                                                                                                                    \
+      FZ_CUDA(launch_pdl(gn_apply_kernel<SL>, dim3(chunks_apply, NB), dim3(kGnThreads), 0, stream, xh, yh, HW, C, groups,               \
+                         frames_per_stat, count_frames, TX, ppc_apply, sums, gamma, beta, eps, silu));                               \
   } while (0)
   if (slots == 1) FZ_GN_LAUNCH(1);
   else if (slots == 2) FZ_GN_LAUNCH(2);
@@ -789,6 +793,26 @@ extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int
 #undef FZ_GN_LAUNCH
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
+}
+
+extern "C" int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, const float* gamma,
+                                     const float* beta, float eps, int silu, void* workspace_f64, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && y && gamma && beta && workspace_f64, "fz_groupnorm: null pointer");
+  return groupnorm_impl(3, x, y, NB, HW, C, groups, frames_per_stat, frames_per_stat, gamma, beta, eps, silu, workspace_f64, nullptr, stream);
+}
+
+// Frame-sharded GroupNorm: statistics and apply as separate calls so that the (sum, sumsq) of the frames held by other
+// GPUs can be all-reduced in between.  fz_groupnorm_stats_f16 leaves float2 sums[NB][groups] at workspace + 768 KiB.
+extern "C" int fz_groupnorm_stats_f16(const void* x, int NB, int HW, int C, int groups, void* workspace_f64, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && workspace_f64, "fz_groupnorm_stats: null pointer");
+  return groupnorm_impl(1, x, nullptr, NB, HW, C, groups, 1, 1, nullptr, nullptr, 0.f, 0, workspace_f64, nullptr, stream);
+}
+
+extern "C" int fz_groupnorm_apply_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, int count_frames,
+                                      const float* gamma, const float* beta, float eps, int silu, const void* image_sums,
+                                      cudaStream_t stream) {
+  FZ_CHECK_ARG(x && y && gamma && beta && image_sums && count_frames >= frames_per_stat, "fz_groupnorm_apply: bad arguments");
+  return groupnorm_impl(2, x, y, NB, HW, C, groups, frames_per_stat, count_frames, gamma, beta, eps, silu, nullptr, image_sums, stream);
 }
 
 extern "C" int fz_layernorm_f16(const void* x, void* y, long long M, int C, const float* gamma, const float* beta, float eps,

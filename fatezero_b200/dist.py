@@ -51,3 +51,41 @@ def shard_frames(num_frames: int, world: int, rank: int) -> List[int]:
 def shard_clips(num_clips: int, world: int, rank: int) -> List[int]:
     """Round-robin clip assignment for the replica mode."""
     return list(range(rank, num_clips, world))
+
+
+def frame_slice(x: torch.Tensor, rank: int, world: int, dim: int = 2) -> torch.Tensor:
+    """This rank's contiguous frame block of a [B, C, F, H, W] clip tensor."""
+    frames = shard_frames(x.shape[dim], world, rank)
+    return x.narrow(dim, frames[0], len(frames)).contiguous()
+
+
+def gather_frames(x_local: torch.Tensor, world: int, dim: int = 2, group=None) -> torch.Tensor:
+    """Inverse of frame_slice on every rank (all-gather over the frame axis)."""
+    import torch.distributed as dist
+    if world <= 1:
+        return x_local
+    parts = [torch.empty_like(x_local) for _ in range(world)]
+    dist.all_gather(parts, x_local.contiguous(), group=group)
+    return torch.cat(parts, dim=dim)
+
+
+def gathered_source_rows(frame_index: List[int], rank: int, world: int, frames_local: int, batch: int) -> List[int]:
+    """Row blocks of the all-gathered K / V^T buffer ([world][batch][frames_local] frames) that the local query frames read:
+    frame_index[g] is the GLOBAL source frame of global query frame g (engine.sc_frame_indices over the whole clip)."""
+    nb = batch * frames_local
+    out = []
+    for b in range(batch):
+        for f in range(frames_local):
+            g = frame_index[rank * frames_local + f]
+            out.append((g // frames_local) * nb + b * frames_local + g % frames_local)
+    return out
+
+
+def allreduce_set_sums(image_sums: torch.Tensor, frames_local: int, group=None) -> torch.Tensor:
+    """GroupNorm statistics exchange: image_sums [batch * frames_local, G, 2] -> [batch, G, 2] summed over the local frames AND the ranks."""
+    import torch.distributed as dist
+    nb, g, two = image_sums.shape
+    s = image_sums.view(nb // frames_local, frames_local, g, two).sum(1)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(s, group=group)
+    return s

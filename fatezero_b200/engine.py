@@ -61,7 +61,41 @@ class UNetEngine:
         self.w: Dict[str, torch.Tensor] = {}
         self._text_key = None
         self._text_kv: Dict[str, tuple] = {}
+        self.shard = None  # frame sharding over GPUs: (rank, world, process group), see set_frame_shard
         self._prepare({k: v.detach() for k, v in unet.state_dict().items()})
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # frame sharding: the frames of ONE clip are split contiguously over the GPUs of one NVSwitch box; every rank
+    # calls forward() with its own frames [B, 4, F/world, H, W].  Exchanges: (1) all-gather of K and V^T over the frame axis for the
+    # sparse-causal self-attention, (2) all-reduce of the GroupNorm (sum, sumsq) of the joint-frame norms.  The temporal LoRA convs and
+    # the temporal attention need frame halos / an all-to-all: supported when they are exact identities (un-tuned SD weights, which is
+    # what the reference's zero-shot configs run), otherwise rejected.
+    # ---------------------------------------------------------------------------------------------------------------
+    def set_frame_shard(self, rank: int, world: int, group=None):
+        if world <= 1:
+            self.shard = None
+            return
+        live = [n for n, skipped in self.lora_skip.items() if not skipped]
+        live += [n for n in self.w if n.endswith(".attn_temporal.qkv") and n[: -len(".transformer_blocks.0.attn_temporal.qkv")] + ".proj_out.bias#folded" not in self.w]
+        live += [n for n in self.w if n.endswith(".conv_temporal.weight")]
+        if live:
+            raise NotImplementedError(
+                "frame sharding needs identity temporal layers (zero LoRA-up / zero attn_temporal.to_out as produced by from_2d_model); "
+                f"{len(live)} temporal layers carry weights (first: {live[0]}): halo / all-to-all exchange for them is not built yet")
+        self.shard = (int(rank), int(world), group)
+
+    def _gn_joint(self, x3: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, F: int, silu: bool) -> torch.Tensor:
+        """nn.GroupNorm over (C/G, F_total, H, W) (resnet.py:338,369; unet_3d_condition.py:439) with the frames of other ranks included."""
+        if self.shard is None:
+            return ops.groupnorm(x3, gamma, beta, eps, self.groups, F, silu)
+        from . import dist as fzdist
+        _, world, group = self.shard
+        NB = x3.shape[0]
+        sums = ops.groupnorm_stats(x3, self.groups)                       # [NB, G, 2] fp32 view into the workspace
+        set_sums = fzdist.allreduce_set_sums(sums, F, group)              # [B, G, 2] over all ranks
+        sums.zero_()
+        sums.view(NB // F, F, self.groups, 2)[:, 0] = set_sums            # the apply kernel adds the F slots of a set
+        return ops.groupnorm_apply(x3, gamma, beta, eps, self.groups, F, F * world, silu, sums)
 
     # ---------------------------------------------------------------------------------------------------------------
     # weight packing
@@ -210,12 +244,12 @@ class UNetEngine:
         """ResnetBlockPseudo3D.forward (resnet.py:335-394)."""
         w = self.w
         NB, H, W, Cin = x.shape
-        n1 = ops.groupnorm(x.view(NB, H * W, Cin), w[p + ".norm1.weight"], w[p + ".norm1.bias"], self.eps, self.groups, F, True)
+        n1 = self._gn_joint(x.view(NB, H * W, Cin), w[p + ".norm1.weight"], w[p + ".norm1.bias"], self.eps, F, True)
         a, b = self.temb_slices[p]
         tb = temb_all[a:b].view(1, b - a)
         h = self.conv(p + ".conv1", n1.view(NB, H, W, Cin), B, F, group_bias=tb)
         Cout = h.shape[-1]
-        n2 = ops.groupnorm(h.view(NB, H * W, Cout), w[p + ".norm2.weight"], w[p + ".norm2.bias"], self.eps, self.groups, F, True)
+        n2 = self._gn_joint(h.view(NB, H * W, Cout), w[p + ".norm2.weight"], w[p + ".norm2.bias"], self.eps, F, True)
         if p + ".conv_shortcut.weight" in w:
             sc = ops.gemm(x.view(-1, Cin), w[p + ".conv_shortcut.weight"], bias=w[p + ".conv_shortcut.bias"]).view(NB, H, W, Cout)
         else:
@@ -242,16 +276,31 @@ class UNetEngine:
             index_list = [-1, "first"]
         if "least_sc_channel" in self.mc and C < self.mc["least_sc_channel"]:
             index_list = []
-        fis = sc_frame_indices(index_list, F) if index_list else [list(range(F))]
-        src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]
         ln1 = ops.layernorm(h, w[bp + ".norm1.weight"], w[bp + ".norm1.bias"])
         vt = torch.empty((NB, heads, d, S), dtype=f16, device=self.dev)
         qk = ops.gemm(ln1, w[bp + ".attn1.qkv"], vt=dict(out=vt, col_start=2 * C, S=S, d=d, heads=heads))
+        k_src, vt_src, n_src = qk[:, C:], vt, NB
+        if self.shard is not None and index_list:
+            # K / V^T of every frame of the clip: NCCL all-gather over the frame axis (attention_register.py:162-193 indexes the whole clip)
+            import torch.distributed as dist
+            rank, world, group = self.shard
+            k_loc = qk[:, C:2 * C].contiguous()
+            k_src = torch.empty((world * M, C), dtype=f16, device=self.dev)
+            vt_src = torch.empty((world * NB, heads, d, S), dtype=f16, device=self.dev)
+            dist.all_gather_into_tensor(k_src, k_loc, group=group)
+            dist.all_gather_into_tensor(vt_src, vt, group=group)
+            n_src = world * NB
+            fis = sc_frame_indices(index_list, F * world)  # indices over the GLOBAL frames; rank r holds [r*F, (r+1)*F)
+            from . import dist as fzdist
+            src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
+        else:
+            fis = sc_frame_indices(index_list, F) if index_list else [list(range(F))]
+            src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]
         o = torch.empty((M, C), dtype=f16, device=self.dev)
         kw = {}
         if ctrl is not None and S <= 32 ** 2:
             kw = ctrl.self_attn_args(place, S, len(src_index) * S, heads, NB, F) or {}
-        ops.attention(qk[:, :C], qk[:, C:], vt, o, S_q=S, keys_per_slot=S, n_src=NB, d=d, heads=heads, F=F, BF=NB, scale=scale,
+        ops.attention(qk[:, :C], k_src, vt_src, o, S_q=S, keys_per_slot=S, n_src=n_src, d=d, heads=heads, F=F, BF=NB, scale=scale,
                       src_index=src_index, **kw)
         h = ops.gemm(o, w[bp + ".attn1.to_out.0.weight"], bias=w[bp + ".attn1.to_out.0.bias"], residual=h)
         # ---- attn2: text cross-attention (attention_register.py:71-128)
@@ -343,7 +392,7 @@ class UNetEngine:
             if i != nblk - 1:
                 h = self.conv(f"{p}.upsamplers.0.conv", ops.upsample2x(h), B, F)
         NBh, Hh, Wh, Ch = h.shape
-        n = ops.groupnorm(h.view(NB, Hh * Wh, Ch), w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.eps, self.groups, F, True)
+        n = self._gn_joint(h.view(NB, Hh * Wh, Ch), w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.eps, F, True)
         co = self.cfg["out_channels"]
         # conv_out as one 16-wide MMA tile (first `co` channels valid); its bias precedes the temporal conv (resnet.py:64 then :76)
         y = ops.conv3x3(n.view(NB, Hh, Wh, Ch), w["conv_out.weight"], bias=w["conv_out.bias"])

@@ -145,6 +145,30 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+def groupnorm_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
+    """Per-image (sum, sumsq) of every group: fp32 view [NB, groups, 2] INTO the shared workspace (valid until the next groupnorm call)."""
+    _chk(x, f16, "groupnorm_stats")
+    NB, HW, Cc = x.shape
+    assert x.is_contiguous()
+    ws = _workspace(x.device, 1 << 20)
+    _lib.call("fz_groupnorm_stats_f16", _p(x), NB, HW, Cc, groups, _p(ws), _stream())
+    off = (768 * 1024) // 4
+    return ws.view(torch.float32)[off: off + NB * groups * 2].view(NB, groups, 2)
+
+
+def groupnorm_apply(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, groups: int, frames_per_stat: int, count_frames: int,
+                    silu: bool, sums: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Second half of the frame-sharded GroupNorm: sums [NB, groups, 2] fp32 (the apply adds frames_per_stat consecutive images)."""
+    _chk(x, f16, "groupnorm_apply")
+    NB, HW, Cc = x.shape
+    assert x.is_contiguous() and sums.is_contiguous() and sums.dtype == torch.float32 and sums.numel() == NB * groups * 2
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("fz_groupnorm_apply_f16", _p(x), _p(out), NB, HW, Cc, groups, frames_per_stat, count_frames, _p(gamma), _p(beta), float(eps),
+              int(silu), _p(sums), _stream())
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     _chk(x, f16, "layernorm")
     M, Cc = x.shape

@@ -256,6 +256,11 @@ class UNetPseudo3DConditionModel(nn.Module):
             self._engine = UNetEngine(self)
         return self._engine
 
+    def set_frame_shard(self, rank: int, world: int, group=None):
+        """Split the frames of one clip over `world` GPUs: every rank then calls forward with ITS frames
+        [B, 4, F/world, H, W]; the engine all-gathers K/V and all-reduces the joint-frame GroupNorm statistics over `group`."""
+        self.engine().set_frame_shard(rank, world, group)
+
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None, return_dict: bool = True):
         if class_labels is not None or attention_mask is not None:
             raise NotImplementedError("class_labels / attention_mask are not supported (attention_register.py:146-151)")

@@ -108,6 +108,14 @@ int fz_attention_f16(const fz_attn_args_t* args, fz_stream_t stream);
  * zero-filled once before the first call and is left consistent by every call (calls sharing it must be stream-ordered). */
 int fz_groupnorm_nhwc_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, const float* gamma,
                           const float* beta, float eps, int silu, void* workspace_f64, fz_stream_t stream);
+
+/* Frame-sharded GroupNorm (one clip's frames over several GPUs; resnet.py:338,369 normalise over ALL frames):
+ * fz_groupnorm_stats_f16 leaves float2 (sum, sumsq) [NB][groups] at workspace_f64 + 768 KiB; the caller all-reduces the per-set sums over
+ * the ranks (NCCL) and passes them to fz_groupnorm_apply_f16 as image_sums (the apply kernel adds frames_per_stat consecutive images of a
+ * set and divides by C/groups * HW * count_frames, count_frames = frames of the set on ALL ranks). */
+int fz_groupnorm_stats_f16(const void* x, int NB, int HW, int C, int groups, void* workspace_f64, fz_stream_t stream);
+int fz_groupnorm_apply_f16(const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, int count_frames,
+                           const float* gamma, const float* beta, float eps, int silu, const void* image_sums, fz_stream_t stream);
 /* nn.LayerNorm over channels of token rows (models/attention.py:281,303,320,331) */
 int fz_layernorm_f16(const void* x, void* y, long long M, int C, const float* gamma, const float* beta, float eps, fz_stream_t stream);
 /* F.interpolate(scale_factor=2, mode="nearest") (resnet.py:145) */

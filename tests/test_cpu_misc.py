@@ -143,3 +143,59 @@ def test_gloo_world_size_2():
     assert res[0][2] == [0, 1, 2, 3] and res[1][2] == [4, 5, 6, 7]
     assert res[0][3] == [0, 2, 4] and res[1][3] == [1, 3]
     assert res[0][4] == 12.0 and res[0][5] == [3.0, 6.0]
+
+
+def _shard_worker(rank, world, port, q):
+    """Frame-sharded exchange logic on CPU tensors (gloo): the all-gathered K rows picked through gathered_source_rows and the
+    all-reduced GroupNorm sums must equal what the unsharded clip computes."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from fatezero_b200 import dist as fzd
+    from fatezero_b200.engine import sc_frame_indices
+    fzd.init("gloo")
+    B, F, S, C, G = 2, 6, 5, 4, 2
+    Fl = F // world
+    g = torch.Generator().manual_seed(0)
+    k_full = torch.randn(B, F, S, C, generator=g)          # K of the whole clip, (b f) order like the engine
+    x_full = torch.randn(B, F, 7, G * 3, generator=g)      # activations for the GroupNorm statistics
+    frames = fzd.shard_frames(F, world, rank)
+    k_loc = k_full[:, frames].reshape(B * Fl * S, C).contiguous()
+    gathered = torch.empty(world * B * Fl * S, C)
+    dist.all_gather_into_tensor(gathered, k_loc)
+    ok = True
+    for index in (["mid"], [-1, "first"], [1, "last"]):
+        for fi in sc_frame_indices(index, F):
+            rows = fzd.gathered_source_rows(fi, rank, world, Fl, B)
+            i = 0
+            for b in range(B):
+                for f in range(Fl):
+                    want = k_full[b, fi[rank * Fl + f]]
+                    got = gathered.view(world * B * Fl, S, C)[rows[i]]
+                    ok = ok and torch.equal(want, got)
+                    i += 1
+    xl = x_full[:, frames].reshape(B * Fl, 7, G, 3)
+    image_sums = torch.stack([xl.sum((1, 3)), (xl * xl).sum((1, 3))], -1)      # [B*Fl, G, 2]
+    s = fzd.allreduce_set_sums(image_sums.contiguous(), Fl)
+    xf = x_full.reshape(B, F * 7, G, 3)
+    want = torch.stack([xf.sum((1, 3)), (xf * xf).sum((1, 3))], -1)
+    ok = ok and torch.allclose(s, want, rtol=1e-5, atol=1e-5)
+    sl = fzd.frame_slice(x_full.permute(0, 3, 1, 2), rank, world, dim=2)       # [B, C, F, H] style tensor
+    back = fzd.gather_frames(sl, world, dim=2)
+    ok = ok and torch.equal(back, x_full.permute(0, 3, 1, 2))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_frame_shard_exchange_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
