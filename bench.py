@@ -187,6 +187,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the one JSON line of the contract
         dist.init_process_group("nccl", device_id=device)
     shard_frames = args.shard == "frames" and world > 1
     # --shard frames: ONE clip, its frames split over the ranks (K/V all-gather + GroupNorm-statistics all-reduce);
