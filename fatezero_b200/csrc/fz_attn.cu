@@ -74,8 +74,8 @@ __device__ __forceinline__ float ex2(float x) {
 // The plain attention kernel is MUFU-bound (16 ex2 / clk / SM, tools/micro/exp_rate.cu), so a quarter of its exponentials take this
 // path (measured: 20.5 exp / clk / SM for the 3:1 mix).
 __device__ __forceinline__ float ex2_poly(float y) {
-  float yr = __fadd_rd(y, 12582912.f);          // 1.5 * 2^23 + floor(y)
-  yr = fmaxf(yr, 12582912.f - 125.f);           // results below 2^-125 are flushed (fp16 rounds them to zero anyway)
+  y = fmaxf(y, -125.f);                         // also maps -inf (masked keys) to 2^-125, which fp16 rounds to zero
+  const float yr = __fadd_rd(y, 12582912.f);    // 1.5 * 2^23 + floor(y)
   const float fl = yr - 12582912.f;
   const float f = y - fl;                       // [0, 1)
   float p = fmaf(0.013534133322536945f, f, 0.05201148986816406f);
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* xchg = reinterpret_cast<float*>(o_full + 2);  // [2 warpgroups][128 rows][2]
 
-  const int tiles_per_slot = p.keys_per_slot >> 7;
+  const int tiles_per_slot = (p.keys_per_slot + 127) >> 7;  // a partial last tile (text cross-attention: 77 keys) is masked below
   const int n_tiles = tiles_per_slot * p.n_slots;
 
   if (threadIdx.x == 0) {
@@ -844,6 +844,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
       FZ_TIMED(1, mbar_wait(&s_full[b], (j / 3) & 1));
       tc_fence_after();
       const uint32_t sbase = tmem_base + lane_addr + b * 128;
+      const int tile_valid = min(128, p.keys_per_slot - ((j % tiles_per_slot) << 7));  // keys beyond it are TMA zero fill: masked to -inf
       uint32_t ra[32], rb[32];
       // ---- tile maximum (TMEM reads are cheap: the scores are read again below instead of being kept in 128 registers) ----
       {
@@ -855,6 +856,11 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
           uint32_t(&cur)[32] = (i & 1) ? rb : ra;
           uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
           if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
+          if (tile_valid < (i + 1) * 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;
+          }
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             c0 = fmaxf(fmaxf(c0, __uint_as_float(cur[e + 0])), __uint_as_float(cur[e + 1]));
@@ -899,6 +905,11 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
         uint32_t(&cur)[32] = (i & 1) ? rb : ra;
         uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
         if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
+        if (tile_valid < (i + 1) * 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;  // exp2(-inf) = 0 on both the MUFU and the polynomial path
+        }
         float* pv = reinterpret_cast<float*>(cur);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -1030,8 +1041,8 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     if (int rc = encode_tmap_f16(&p.tmVt, a->vt, 4, dims, strides, box, true)) return rc;
   }
   // rows without any controller hook and a small head dim take the TMEM-resident-P kernel
-  const bool plain = (a->row_mode == FZ_ATTN_NONE || a->edit_bf_start >= a->BF) && !a->acc && a->d <= 64 && a->keys_per_slot % 128 == 0 &&
-                     a->S_q % 128 == 0;
+  const bool plain = (a->row_mode == FZ_ATTN_NONE || a->edit_bf_start >= a->BF) && !a->acc && a->d <= 64 &&
+                     (a->keys_per_slot % 128 == 0 || a->n_slots == 1) && a->S_q % 128 == 0;
   if (plain) {
     uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->keys_per_slot, (uint64_t)a->n_src};
     uint64_t strides[3] = {(uint64_t)a->d, (uint64_t)a->ldk, (uint64_t)a->ldk * a->keys_per_slot};

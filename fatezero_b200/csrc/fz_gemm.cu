@@ -554,7 +554,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-    if (p.use_tma_store && lane == 0) tma_store_wait_all<0>();
+    // the staging slots must stay valid until the bulk stores have READ them; their global writes complete with the grid
+    // (kernel boundary / griddepcontrol.wait of the dependent), as in CUTLASS' store_tail
+    if (p.use_tma_store && lane == 0) tma_store_wait_read<0>();
 #ifdef FZ_GEMM_PROFILE
     if (gp_on && warp == 2 && lane == 0) {
       g_gemm_dbg[0] = GP_NOW() - gp_e0;
