@@ -28,8 +28,8 @@ for (M, N, K) in [(65536, 320, 320), (32768, 320, 320), (65536, 960, 320), (6553
 if not only:
     for (M, N, K) in [(65536, 320, 320), (65536, 320, 1280), (16384, 640, 640), (4096, 1280, 1280)]:
         a = torch.randn(M, K, device=dev).half(); w = torch.randn(N, K, device=dev).half(); out = torch.empty(M, N, device=dev, dtype=torch.float16)
-        res = torch.randn(M, N, device=dev).half(); bias = torch.randn(N, device=dev)
-        ms = timeit(lambda: ops.gemm(a, w, bias=bias, residual=res, out=out))
+        skip = torch.randn(M, N, device=dev).half(); bias = torch.randn(N, device=dev)
+        ms = timeit(lambda: ops.gemm(a, w, bias=bias, residual=skip, out=out))
         print(dict(op="gemm+bias+residual", M=M, N=N, K=K, us=ms * 1e3, tflops=2 * M * N * K / ms / 1e9), flush=True)
     for (B, F, HW, Cin, Cout) in [(2, 8, 4096, 320, 160), (2, 8, 4096, 160, 320), (2, 8, 1024, 640, 160), (2, 8, 1024, 160, 640), (2, 8, 256, 1280, 160), (2, 8, 256, 160, 1280), (2, 8, 64, 1280, 160), (2, 8, 64, 160, 1280)]:
         x = torch.randn(B, F, HW, Cin, device=dev).half(); w3 = torch.randn(3, Cout, Cin, device=dev).half()
