@@ -996,6 +996,7 @@ static int encode_cache_map(CUtensorMap* tm, const void* base, int keys_ld_slot,
 }
 
 extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
+  if (int rc = check_single_device()) return rc;
   FZ_CHECK_ARG(a && a->q && a->k && a->vt && a->out, "fz_attention: null pointer");
   FZ_CHECK_ARG(a->d % 8 == 0 && a->d >= 8 && a->d <= 192, "fz_attention: head dim %d unsupported", a->d);
   FZ_CHECK_ARG(a->n_slots >= 1 && a->n_slots <= kMaxSlots && a->BF <= kMaxBF, "fz_attention: n_slots=%d BF=%d unsupported", a->n_slots, a->BF);

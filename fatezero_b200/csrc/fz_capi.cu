@@ -77,6 +77,23 @@ int encode_tmap_f16_sw(CUtensorMap* out, const void* base, int rank, const uint6
 
 }  // namespace fz
 
+namespace fz {
+int check_single_device() {
+  static int first = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device");
+    return FZ_ERR_CUDA;
+  }
+  if (first < 0) first = dev;
+  if (dev != first) {
+    set_error("libfatezero_b200 was first used on device %d and is now called on device %d: it caches per-device state, run one process per GPU", first, dev);
+    return FZ_ERR_INVALID;
+  }
+  return FZ_OK;
+}
+}  // namespace fz
+
 extern "C" const char* fz_last_error(void) { return fz::g_err; }
 extern "C" int fz_version(void) { return 100; }
 extern "C" int fz_device_check(void) {

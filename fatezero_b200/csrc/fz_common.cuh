@@ -15,6 +15,9 @@ namespace fz {
 // error plumbing (C-ABI returns int; message kept per thread)
 // ---------------------------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// The library caches per-device state (kernel attributes, SM count, the skip-folding selection table): one process per GPU.
+// Returns FZ_OK on the device of the first call, FZ_ERR_INVALID (with an error message) on any other device.
+int check_single_device();
 #define FZ_OK 0
 #define FZ_ERR_INVALID 1
 #define FZ_ERR_CUDA 2

@@ -756,6 +756,7 @@ using namespace fz;
 static int groupnorm_impl(int which, const void* x, void* y, int NB, int HW, int C, int groups, int frames_per_stat, int count_frames,
                           const float* gamma, const float* beta, float eps, int silu, void* workspace_f64, const void* sums_in,
                           cudaStream_t stream) {
+  if (int rc = check_single_device()) return rc;
   FZ_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64, "fz_groupnorm: C=%d groups=%d unsupported", C, groups);
   FZ_CHECK_ARG(frames_per_stat >= 1 && NB % frames_per_stat == 0, "fz_groupnorm: NB %% frames_per_stat != 0");
   int TX, slots, ppc, chunks, ppc_apply, chunks_apply;

@@ -665,6 +665,7 @@ static int fold_residuals(TapGemmParams& p, int bn, cudaStream_t stream) {
 }
 
 static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cudaStream_t stream) {
+  if (int rc = check_single_device()) return rc;
   // output tensor map for the TMA-store epilogue ([M, N_out] row-major, row stride ldo)
   p.use_tma_store = 0;
   if (p.rows_per_tile % 32 == 0 && p.ldo % 8 == 0 && p.N % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
