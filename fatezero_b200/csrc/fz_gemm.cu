@@ -34,6 +34,7 @@ struct TapGemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmC;    // output [M, N] as (cols, rows), box {32 cols, 32 rows}, SWIZZLE_64B (epilogue TMA stores)
+  CUtensorMap tmC16;  // same output with box {16 cols, 32 rows}, no swizzle (GEGLU epilogue with 16-column chunks)
   CUtensorMap tmR[2]; // skip tensors [M, N] folded into the accumulator as extra k-blocks: box {64 cols, 128 rows}
   CUtensorMap tmE;    // identity blocks E[j][n][k] = (n == 64 j + k): (k : 64, n : 256, j : 4), box {64, BLOCK_N, 1}
   int n_res;          // number of folded skip tensors (0..2); the epilogue then sees residual == residual2 == null
@@ -105,8 +106,10 @@ __device__ long long g_gemm_dbg[16];
 #define GP_ADD(slot, expr) do { } while (0)
 #endif
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+// EPI_GROUPS = epilogue warps per TMEM lane quadrant: 2 (320 threads) for every row-major epilogue; 4 (576 threads, 16-column chunks so that
+// the kernel fits the smaller register budget) for the GEGLU epilogue, which is ALU-bound: it was 3x the mainloop with two warps per scheduler.
+template <int BLOCK_N, int EPI_GROUPS = 2>
+__global__ void __launch_bounds__(64 + 128 * EPI_GROUPS, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   using Cfg = TapGemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 8);
+      mbar_init(&tempty[b], 4 * EPI_GROUPS);
     }
     fence_mbar_init();
   }
@@ -249,12 +252,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     // the v0 epilogue spent ~46 instructions per output element on per-element bound / option branches (ncu: 7 % tensor pipe
     // on K=320 GEMMs); edge tiles fall back to the generic masked path.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;  // two warps per quadrant take alternating column chunks
+    const int half = (warp - 2) >> 2;  // the EPI_GROUPS warps of a quadrant take alternating column chunks
     const int row_in_tile = quad * 32 + lane;
     // Coalesced output path: each warp stages its 32 rows x 32 columns (64 B rows, 64-byte swizzle => conflict-free 16-byte
     // st.shared) and one lane issues a TMA store; direct per-row 16-byte stores touch 32 lines per instruction and made the
     // epilogue LSU-bound (~2.4 us per 128x160 tile).
-    uint8_t* my_epi = epi_smem + (warp - 2) * 2 * 2048;
+    constexpr int kSlotBytes = (EPI_GROUPS == 4) ? 1024 : 2048;  // 32 rows x (16 | 32) fp16 columns
+    uint8_t* my_epi = epi_smem + (warp - 2) * 2 * kSlotBytes;
     uint32_t epi_count = 0;
     auto store_chunk32 = [&](const uint4 (&o)[4], long long m_row, int col, int m_warp0, uint8_t* acquired) {
       if (p.use_tma_store) {
@@ -286,6 +290,34 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         uint4* op = reinterpret_cast<uint4*>(p.out + m_row * p.ldo + col);
 #pragma unroll
         for (int j = 0; j < 4; ++j) op[j] = o[j];
+      }
+    };
+    // 16-column variant (GEGLU with 16 epilogue warps): 32-byte rows, no swizzle, tensor map tmC16 with box {16, 32}
+    auto store_chunk16 = [&](const uint4 (&o)[2], long long m_row, int col, int m_warp0) {
+      if (p.use_tma_store) {
+        uint8_t* slot = my_epi + (epi_count & 1) * kSlotBytes;
+        const long long gp_a = GP_NOW();
+        if (epi_count >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
+        const long long gp_b = GP_NOW();
+        GP_ADD(4, gp_b - gp_a);
+        *reinterpret_cast<uint4*>(slot + lane * 32) = o[0];
+        *reinterpret_cast<uint4*>(slot + lane * 32 + 16) = o[1];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmC16, slot, col, m_warp0);
+          tma_store_commit();
+        }
+        ++epi_count;
+        GP_ADD(5, GP_NOW() - gp_b);
+        GP_ADD(6, 1);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(p.out + m_row * p.ldo + col);
+        op[0] = o[0];
+        op[1] = o[1];
       }
     };
     // Coalesced residual fetch: lane l reads the 16-byte piece (l & 3) of rows (l >> 2) + 8 i of the warp's 32 x 32 block (8 lines
@@ -338,10 +370,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BLOCK_N;
       if (p.mode == FZ_EPI_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
-        constexpr int CH = (HALF >= 32) ? 32 : 16;
+        constexpr int CH = (HALF >= 32 && EPI_GROUPS == 2) ? 32 : 16;
         if constexpr (HALF >= 16) {
 #pragma unroll 1
-          for (int c = half * CH; c < HALF; c += 2 * CH) {
+          for (int c = half * CH; c < HALF; c += EPI_GROUPS * CH) {
             uint32_t xa[CH], ga[CH];
             const long long gp_l = GP_NOW();
             if constexpr (CH == 32) {
@@ -357,7 +389,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             const int ocol0 = nt * HALF + c;
             const int m_warp0 = mt * p.rows_per_tile + quad * 32;
             const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
-            if (warp_ok && ocol0 + CH <= p.N && (row_ok || (p.use_tma_store && CH == 32))) {
+            if (warp_ok && ocol0 + CH <= p.N && (row_ok || (p.use_tma_store && (CH == 32 || EPI_GROUPS == 4)))) {
               float xv[CH], gv[CH];
 #pragma unroll
               for (int e = 0; e < CH; ++e) { xv[e] = __uint_as_float(xa[e]); gv[e] = __uint_as_float(ga[e]); }
@@ -386,6 +418,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               GP_ADD(3, GP_NOW() - gp_c);
               if constexpr (CH == 32) {
                 store_chunk32(o, m, ocol0, m_warp0, nullptr);
+              } else if constexpr (EPI_GROUPS == 4) {
+                store_chunk16(o, m, ocol0, m_warp0);
               } else {
                 uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + ocol0);
 #pragma unroll
@@ -404,13 +438,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             }
           }
         }
-      } else {
+      } else if constexpr (EPI_GROUPS == 2) {  // (the 16-epilogue-warp instantiation is GEGLU-only)
         constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
         const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
         uint4 preA[4], preB[4];
         bool have_pre = false;
 #pragma unroll 1
-        for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
+        for (int c = half * CH; c < BLOCK_N; c += EPI_GROUPS * CH) {
           uint32_t acc[CH];
           const long long gp_l = GP_NOW();
           const int col0 = nt * BLOCK_N + c;
@@ -586,19 +620,27 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
-static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+template <int BN, int EG>
+static int launch_tapgemm_eg(const TapGemmParams& p, cudaStream_t stream) {
   using Cfg = TapGemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    FZ_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FZ_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  FZ_CUDA(launch_pdl(tapgemm_kernel<BN>, dim3(grid), dim3(320), Cfg::kSmemBytes, stream, p));
+  FZ_CUDA(launch_pdl(tapgemm_kernel<BN, EG>, dim3(grid), dim3(64 + 128 * EG), Cfg::kSmemBytes, stream, p));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
+}
+
+template <int BN>
+static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  if constexpr (BN >= 64) {
+    if (p.mode == FZ_EPI_GEGLU && p.use_tma_store == 2) return launch_tapgemm_eg<BN, 4>(p, stream);
+  }
+  return launch_tapgemm_eg<BN, 2>(p, stream);
 }
 
 static int pick_block_n(int gemm_cols, int mode, int forced, int m_tiles) {
@@ -675,6 +717,11 @@ static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cuda
     uint32_t box[2] = {32, 32};
     if (int rc = encode_tmap_f16_sw(&p.tmC, p.out, 2, dims, strides, box, 64)) return rc;
     p.use_tma_store = 1;
+    if (p.mode == FZ_EPI_GEGLU && p.N % 16 == 0) {
+      uint32_t box16[2] = {16, 32};
+      if (int rc = encode_tmap_f16_sw(&p.tmC16, p.out, 2, dims, strides, box16, 0)) return rc;
+      p.use_tma_store = 2;  // both maps valid: the GEGLU launch may take the 16-epilogue-warp instantiation
+    }
   }
   const int bn = pick_block_n(gemm_cols, p.mode, forced_bn, p.m_tiles);
   p.n_tiles = (gemm_cols + bn - 1) / bn;
