@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(64 + 128 * EPI_GROUPS, 1) tapgemm_kernel(const
             }
           }
         }
-      } else if constexpr (EPI_GROUPS == 2) {  // (the 16-epilogue-warp instantiation is GEGLU-only)
-        constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+      } else {
+        constexpr int CH = (BLOCK_N >= 32 && EPI_GROUPS == 2) ? 32 : 16;
         const float* gb = p.group_bias ? p.group_bias + (m / p.rows_per_group) * p.N : nullptr;
         uint4 preA[4], preB[4];
         bool have_pre = false;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI_GROUPS, 1) tapgemm_kernel(const
           const bool warp_ok = quad * 32 < p.rows_per_tile && m_warp0 < p.M;
           if (!warp_ok || col0 >= p.N) continue;
           const bool fast = col0 + CH <= p.N && col0 + CH <= p.vt_col_start;
-          if (fast && (row_ok || (p.use_tma_store && CH == 32))) {
+          if (fast && (row_ok || (p.use_tma_store && (CH == 32 || EPI_GROUPS == 4)))) {
             // ---------------- fast path: full chunk, row-major output ----------------
             float v[CH];
 #pragma unroll
@@ -538,6 +538,8 @@ __global__ void __launch_bounds__(64 + 128 * EPI_GROUPS, 1) tapgemm_kernel(const
             GP_ADD(3, GP_NOW() - gp_c);
             if constexpr (CH == 32) {
               store_chunk32(o, m, col0, m_warp0, slot);
+            } else if constexpr (EPI_GROUPS == 4) {
+              store_chunk16(o, m, col0, m_warp0);
             } else {
               uint4* op = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
 #pragma unroll
@@ -638,7 +640,10 @@ static int launch_tapgemm_eg(const TapGemmParams& p, cudaStream_t stream) {
 template <int BN>
 static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   if constexpr (BN >= 64) {
-    if (p.mode == FZ_EPI_GEGLU && p.use_tma_store == 2) return launch_tapgemm_eg<BN, 4>(p, stream);
+    // 16 epilogue warps (16-column chunks, 96 registers) for the ALU-bound GEGLU epilogue.  Measured and rejected for the short-K
+    // row-major GEMMs: their chunks are latency-bound (~860 cycles per chunk whether it is 16 or 32 columns wide), so twice the warps on
+    // half-size chunks gain nothing (65536x320x320: epilogue warp 29.1k -> 39.5k cycles).
+    if (p.use_tma_store == 2 && p.mode == FZ_EPI_GEGLU) return launch_tapgemm_eg<BN, 4>(p, stream);
   }
   return launch_tapgemm_eg<BN, 2>(p, stream);
 }
@@ -717,7 +722,7 @@ static int dispatch_tapgemm(TapGemmParams& p, int gemm_cols, int forced_bn, cuda
     uint32_t box[2] = {32, 32};
     if (int rc = encode_tmap_f16_sw(&p.tmC, p.out, 2, dims, strides, box, 64)) return rc;
     p.use_tma_store = 1;
-    if (p.mode == FZ_EPI_GEGLU && p.N % 16 == 0) {
+    if (p.N % 16 == 0 && (p.vt_col_start == INT_MAX || p.vt_col_start % 16 == 0)) {
       uint32_t box16[2] = {16, 32};
       if (int rc = encode_tmap_f16_sw(&p.tmC16, p.out, 2, dims, strides, box16, 0)) return rc;
       p.use_tma_store = 2;  // both maps valid: the GEGLU launch may take the 16-epilogue-warp instantiation
