@@ -180,6 +180,10 @@ def instrument_tapgemm(pipe, x0_dev, emb_src):
 
 def run_gpu(args):
     import torch.distributed as dist
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are redirected to stderr for the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     from fatezero_b200 import _lib, synth
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,8 +191,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the one JSON line of the contract
         dist.init_process_group("nccl", device_id=device)
     shard_frames = args.shard == "frames" and world > 1
     # --shard frames: ONE clip, its frames split over the ranks (K/V all-gather + GroupNorm-statistics all-reduce);
@@ -283,6 +285,8 @@ def run_gpu(args):
                     clocks=clocks, e2e=dict(value=round(e2e_value, 4), unit="frames/s", h2d_bytes_per_step=x0_host.numel() * 4,
                                             d2h_bytes_per_step=out_host.numel() * 4),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
