@@ -95,6 +95,24 @@ def test_self_plain(BF, F_, S, heads, d, kind, report):
     check(out, pv(p, gather_v(v, S, heads, d, si)), report, f"self_plain_{S}_{d}_{kind}", atol=4e-3, rtol=4e-3)
 
 
+@pytest.mark.parametrize("ramp", ["up", "down", "spike"])
+def test_self_plain_online_rescale(ramp, report):
+    """The hook-free kernel raises its reference maximum lazily (only when a 128-key tile exceeds it by 2^8) and then rescales O and
+    the row sum: key blocks with growing / shrinking / one spiking scale force that path (random inputs alone never trigger it)."""
+    BF, F_, S, heads, d = 2, 2, 640, 2, 40
+    q, k, v, vt = make_inputs(BF, S, S, BF, heads, d, seed=21, qscale=2.0)
+    kk = k.float().reshape(BF, S, heads * d)
+    for t in range(S // 128):
+        f = {"up": 1.0 + 2.5 * t, "down": 1.0 + 2.5 * (S // 128 - 1 - t), "spike": 9.0 if t == 3 else 1.0}[ramp]
+        kk[:, 128 * t:128 * (t + 1)] *= f
+    k = kk.reshape(BF * S, heads * d).half()
+    si = index_list("own", F_, BF)
+    out = torch.zeros(BF * S, heads * d, dtype=torch.float16, device=dev)
+    ops.attention(q, k, vt, out, S_q=S, keys_per_slot=S, n_src=BF, d=d, heads=heads, F=F_, BF=BF, scale=d ** -0.5, src_index=si)
+    p = ref_probs(q, k, BF, S, S, heads, d, si, d ** -0.5)
+    check(out, pv(p, gather_v(v, S, heads, d, si)), report, f"self_plain_rescale_{ramp}", atol=4e-3, rtol=4e-3)
+
+
 @pytest.mark.parametrize("BF,F_,S,heads,d,kind", [c for c in SELF_CASES if c[2] <= 1024])
 def test_self_store_replace_blend(BF, F_, S, heads, d, kind, report):
     q, k, v, vt = make_inputs(BF, S, S, BF, heads, d, seed=3, qscale=2.0)
