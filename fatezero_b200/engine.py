@@ -283,16 +283,34 @@ class UNetEngine:
         if self.shard is not None and index_list:
             # K / V^T of every frame of the clip: NCCL all-gather over the frame axis (attention_register.py:162-193 indexes the whole clip)
             import torch.distributed as dist
-            rank, world, group = self.shard
-            k_loc = qk[:, C:2 * C].contiguous()
-            k_src = torch.empty((world * M, C), dtype=f16, device=self.dev)
-            vt_src = torch.empty((world * NB, heads, d, S), dtype=f16, device=self.dev)
-            dist.all_gather_into_tensor(k_src, k_loc, group=group)
-            dist.all_gather_into_tensor(vt_src, vt, group=group)
-            n_src = world * NB
-            fis = sc_frame_indices(index_list, F * world)  # indices over the GLOBAL frames; rank r holds [r*F, (r+1)*F)
             from . import dist as fzdist
-            src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
+            rank, world, group = self.shard
+            fis = sc_frame_indices(index_list, F * world)  # indices over the GLOBAL frames; rank r holds [r*F, (r+1)*F)
+            if all(isinstance(ix, str) for ix in index_list):
+                # 'first' / 'mid' / 'last': every query frame reads the SAME source frame -> broadcast that one frame's K / V^T from its
+                # owner (1/F_total of the all-gather bytes); slot s of the source buffer holds [B] frames
+                k_src = torch.empty((len(fis) * B * S, C), dtype=f16, device=self.dev)
+                vt_src = torch.empty((len(fis) * B, heads, d, S), dtype=f16, device=self.dev)
+                for sl, fi in enumerate(fis):
+                    owner, gl = fi[0] // F, fi[0] % F
+                    kb, vb = k_src[sl * B * S:(sl + 1) * B * S], vt_src[sl * B:(sl + 1) * B]
+                    if owner == rank:
+                        kb.view(B, S, C).copy_(qk.view(B, F, S, qk.shape[1])[:, gl, :, C:2 * C])
+                        vb.copy_(vt.view(B, F, heads, d, S)[:, gl])
+                    src = dist.get_global_rank(group, owner) if group is not None else owner
+                    dist.broadcast(kb, src=src, group=group)
+                    dist.broadcast(vb, src=src, group=group)
+                n_src = len(fis) * B
+                src_index = [[sl * B + b for b in range(B) for _ in range(F)] for sl in range(len(fis))]
+            else:
+                # relative indices (-1, +1, ...): NCCL all-gather of K and V^T over the frame axis
+                k_loc = qk[:, C:2 * C].contiguous()
+                k_src = torch.empty((world * M, C), dtype=f16, device=self.dev)
+                vt_src = torch.empty((world * NB, heads, d, S), dtype=f16, device=self.dev)
+                dist.all_gather_into_tensor(k_src, k_loc, group=group)
+                dist.all_gather_into_tensor(vt_src, vt, group=group)
+                n_src = world * NB
+                src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
         else:
             fis = sc_frame_indices(index_list, F) if index_list else [list(range(F))]
             src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]

@@ -14,10 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="frame sharding needs >= 2 GPUs")
-def test_frame_sharded_matches_single_gpu(report):
+@pytest.mark.parametrize("index", ["gather", "const"])
+def test_frame_sharded_matches_single_gpu(index, report):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tools", "shard_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29517" if index == "gather" else "29518", os.path.join(ROOT, "tools", "shard_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FZ_SHARD_INDEX=index))
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert line, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(line[-1])

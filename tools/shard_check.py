@@ -24,7 +24,9 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     fzdist.init("nccl", dev)
-    mc = dict(lora=160, SparseCausalAttention_index=["mid", -1, "first"], least_sc_channel=64)
+    # FZ_SHARD_INDEX=const: only constant source frames ('mid', 'first') -> the broadcast path; default: a relative index too -> all-gather
+    index = ["mid", "first"] if os.environ.get("FZ_SHARD_INDEX") == "const" else ["mid", -1, "first"]
+    mc = dict(lora=160, SparseCausalAttention_index=index, least_sc_channel=64)
     frames, size = 4, 32
     pipe = build_product("mini", mc, device=dev, degenerate_temporal=True)
     cfg = synth.UNET_CONFIGS["mini"]
@@ -70,7 +72,7 @@ def main():
     out["inv_rel"] = ((inv_got - inv_full).abs().max() / inv_full.abs().max()).item()
     out["edit_rel"] = ((edit_got - edit_full).abs().max() / edit_full.abs().max()).item()
     ok = out["forward_max_abs"] <= 2e-3 * max(out["forward_ref_max"], 1.0) and out["inv_rel"] <= 5e-3 and out["edit_rel"] <= 5e-2
-    out.update(world=world, frames=frames, ok=bool(ok))
+    out.update(world=world, frames=frames, index=index, ok=bool(ok))
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
