@@ -21,4 +21,10 @@ CASES = {
         unet="mini", model_config=dict(lora=160),
         frames=3, size=32, steps=3, source="a silver jeep driving down a curvy road", target="a red jeep driving down a curvy road",
         p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.7, "red": 0.4}, self_replace_steps=0.7)),
+    # Replace + Reweight (equalizer on a swapped word) with ['first', +1] K/V frames (a forward-looking relative index) on 4 frames
+    "mini_reweight_next": dict(
+        unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["first", 1], least_sc_channel=128),
+        frames=4, size=32, steps=4, source=SRC, target="a silver jeep driving down a snowy road in the countryside",
+        p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.6}, self_replace_steps=0.5,
+                 eq_params={"words": ["snowy"], "values": [3.0]})),
 }
