@@ -27,4 +27,18 @@ CASES = {
         frames=4, size=32, steps=4, source=SRC, target="a silver jeep driving down a snowy road in the countryside",
         p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.6}, self_replace_steps=0.5,
                  eq_params={"words": ["snowy"], "values": [3.0]})),
+    # ---- oracle-pinning only (gpu=False: the CUDA parity tests skip them; they widen what the CPU oracle is held to) ----
+    # Refine + latent blend WITHOUT self-attention blend, ['last', -1] K/V frames (the blender needs the 16x16 maps: 64x64 latents)
+    "pin_refine_latent_blend": dict(
+        gpu=False, unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["last", -1], least_sc_channel=128),
+        frames=2, size=64, steps=3, source=SRC, target="a silver jeep driving down a curvy road in the snowy countryside",
+        p2p=dict(is_replace_controller=False, cross_replace_steps={"default_": 0.7}, self_replace_steps=0.4,
+                 blend_words=[["jeep"], ["jeep"]], blend_latents=True, blend_th=[0.9, 0.9])),
+    # Replace on the wider 'mid' UNet geometry (attention at more channel counts), default [-1, 'first'] frames
+    "pin_mid_replace": dict(
+        gpu=False, unet="mid", model_config=dict(lora=160, least_sc_channel=320),
+        frames=2, size=32, steps=3, source="a silver jeep driving down a curvy road", target="a silver tank driving down a curvy road",
+        p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.6,
+                 eq_params={"words": ["silver", "tank"], "values": [2.0, 4.0]})),
 }
+GPU_CASES = [k for k, v in CASES.items() if v.get("gpu", True)]
