@@ -165,10 +165,14 @@ class AttentionStore(AttentionControl):
     def between_steps(self):
         self._self_sum_cache = None
         if self.disk_store:
+            # attention_store.py:103-106: the step dict goes to disk and the list holds its PATH; the HBM slabs are released here
+            # (the running cross sums stay: they are what `attention_store` / the latent blend read)
             path = self.store_dir + f"/{self.cur_step:03d}.pt"
             torch.save({k: [t.cpu() for t in v] for k, v in self.step_store.items()}, path)
             self.attention_store_paths.append(path)
-        self.attention_store_all_step.append(self.step_store)
+            self.attention_store_all_step.append(path)
+        else:
+            self.attention_store_all_step.append(self.step_store)
         self.step_store = self.get_empty_store()
 
     @property
@@ -184,6 +188,8 @@ class AttentionStore(AttentionControl):
                 for k in ("down_self", "mid_self", "up_self"):
                     per_pos = None
                     for d in self.attention_store_all_step:
+                        if isinstance(d, str):
+                            d = torch.load(d)
                         cur = d.get(k, [])
                         per_pos = [t.clone() for t in cur] if per_pos is None else [a + b for a, b in zip(per_pos, cur)]
                     sums[k] = per_pos or []
@@ -201,6 +207,8 @@ class AttentionStore(AttentionControl):
         super().reset()
         self.step_store = self.get_empty_store()
         self.attention_store_all_step = []
+        self.attention_store_paths = []
+        self.latents_store = []
         self._acc = {}
         self._self_sum_cache = None
 

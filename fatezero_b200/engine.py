@@ -61,6 +61,7 @@ class UNetEngine:
         self.w: Dict[str, torch.Tensor] = {}
         self._text_key = None
         self._text_kv: Dict[str, tuple] = {}
+        self._foreign = None  # reference-protocol controller of the current forward (slow path), see _foreign_attention
         self.shard = None  # frame sharding over GPUs: (rank, world, process group), see set_frame_shard
         self._prepare({k: v.detach() for k, v in unet.state_dict().items()})
 
@@ -316,21 +317,29 @@ class UNetEngine:
             src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]
         o = torch.empty((M, C), dtype=f16, device=self.dev)
         kw = {}
-        if ctrl is not None and S <= 32 ** 2:
-            kw = ctrl.self_attn_args(place, S, len(src_index) * S, heads, NB, F) or {}
-        ops.attention(qk[:, :C], k_src, vt_src, o, S_q=S, keys_per_slot=S, n_src=n_src, d=d, heads=heads, F=F, BF=NB, scale=scale,
-                      src_index=src_index, **kw)
+        if self._foreign is not None:
+            self._foreign_attention(False, place, qk[:, :C], k_src, vt_src, o, S_q=S, keys_per_slot=S, n_src=n_src, d=d, heads=heads, F=F,
+                                    BF=NB, scale=scale, src_index=src_index)
+        else:
+            if ctrl is not None and S <= 32 ** 2:
+                kw = ctrl.self_attn_args(place, S, len(src_index) * S, heads, NB, F) or {}
+            ops.attention(qk[:, :C], k_src, vt_src, o, S_q=S, keys_per_slot=S, n_src=n_src, d=d, heads=heads, F=F, BF=NB, scale=scale,
+                          src_index=src_index, **kw)
         h = ops.gemm(o, w[bp + ".attn1.to_out.0.weight"], bias=w[bp + ".attn1.to_out.0.bias"], residual=h)
         # ---- attn2: text cross-attention (attention_register.py:71-128)
         ln2 = ops.layernorm(h, w[bp + ".norm2.weight"], w[bp + ".norm2.bias"])
         q2 = ops.gemm(ln2, w[bp + ".attn2.to_q.weight"])
         kt, vtt = self._text_kv[bp + ".attn2"]
         kw = {}
-        if ctrl is not None and S <= 32 ** 2:
-            kw = ctrl.cross_attn_args(place, S, heads, NB, F) or {}
         o2 = torch.empty((M, C), dtype=f16, device=self.dev)
-        ops.attention(q2, kt, vtt, o2, S_q=S, keys_per_slot=77, n_src=B, d=d, heads=heads, F=F, BF=NB, scale=scale,
-                      src_index=[[b for b in range(B) for _ in range(F)]], **kw)
+        if self._foreign is not None:
+            self._foreign_attention(True, place, q2, kt, vtt, o2, S_q=S, keys_per_slot=77, n_src=B, d=d, heads=heads, F=F, BF=NB, scale=scale,
+                                    src_index=[[b for b in range(B) for _ in range(F)]])
+        else:
+            if ctrl is not None and S <= 32 ** 2:
+                kw = ctrl.cross_attn_args(place, S, heads, NB, F) or {}
+            ops.attention(q2, kt, vtt, o2, S_q=S, keys_per_slot=77, n_src=B, d=d, heads=heads, F=F, BF=NB, scale=scale,
+                          src_index=[[b for b in range(B) for _ in range(F)]], **kw)
         h = ops.gemm(o2, w[bp + ".attn2.to_out.0.weight"], bias=w[bp + ".attn2.to_out.0.bias"], residual=h)
         # ---- feed-forward (GEGLU)
         ln3 = ops.layernorm(h, w[bp + ".norm3.weight"], w[bp + ".norm3.bias"])
@@ -349,6 +358,23 @@ class UNetEngine:
         out = ops.gemm(h, w[p + ".proj_out.weight"], bias=po_bias, residual=xr)
         return out.view(NB, H, W, C)
 
+    def _foreign_attention(self, is_cross: bool, place: str, q, k, vt, o, **geo):
+        """Slow path for a controller that only implements the reference protocol `controller(attn[BF, heads, s, t], is_cross, place)`
+        (attention_register.py:49-51): the kernel materialises the fp16 probabilities of EVERY attention layer into a slab (STORE mode on
+        all rows), the Python controller sees / edits that tensor, and a second launch multiplies the (possibly edited) slab with V
+        (REPLACE mode).  This is the reference's own data flow (one probability tensor per layer in HBM) and costs what it costs there;
+        the controllers of fatezero_b200.controllers never take this path."""
+        BF, heads, S = geo["BF"], geo["heads"], geo["S_q"]
+        T = len(geo["src_index"]) * geo["keys_per_slot"]
+        ld = (T + 7) // 8 * 8
+        slab = torch.zeros((BF, heads, S, ld), dtype=f16, device=self.dev)
+        ops.attention(q, k, vt, o, edit_bf_start=0, row_mode=_lib.ATTN_STORE, store=slab, cache_ld=ld, **geo)
+        view = slab[..., :T]
+        new = self._foreign(view, is_cross, place)
+        if new is not None and (new.data_ptr() != view.data_ptr() or new.shape != view.shape):
+            view.copy_(new.reshape(view.shape))
+        ops.attention(q, k, vt, o, edit_bf_start=0, row_mode=_lib.ATTN_REPLACE, base=slab, cache_ld=ld, **geo)
+
     def time_embedding(self, t: float) -> torch.Tensor:
         """time_proj + time_embedding + all time_emb_proj(SiLU(emb)) rows (unet_3d_condition.py:356-362; resnet.py:355)."""
         w = self.w
@@ -362,13 +388,16 @@ class UNetEngine:
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: float, text: torch.Tensor, ctrl=None) -> torch.Tensor:
         """x [B,4,F,H,W] (any float dtype, CUDA), text [B,77,D] -> eps [B,4,F,H,W] fp32."""
+        self._foreign = None
         if ctrl is not None and not hasattr(ctrl, "self_attn_args"):
             if type(ctrl).__name__ in ("EmptyControl", "DummyController"):
                 ctrl = None
+            elif callable(ctrl):
+                self._foreign, ctrl = ctrl, None  # reference-protocol controller: materialised-probability slow path
             else:
                 raise NotImplementedError(
-                    f"controller {type(ctrl).__name__} does not implement the fused-kernel protocol (self_attn_args / cross_attn_args); "
-                    "use the controllers of video_diffusion.prompt_attention.attention_util")
+                    f"controller {type(ctrl).__name__} implements neither the fused-kernel protocol (self_attn_args / cross_attn_args) "
+                    "nor the reference protocol __call__(attn, is_cross, place_in_unet)")
         w = self.w
         B, Cl, F, H, W = x.shape
         NB = B * F

@@ -347,8 +347,15 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
         self.scheduler.set_timesteps(num_inference_steps, device=device)
         timesteps = [int(t) for t in self.scheduler.timesteps]
         if latents is None:
-            latents = self.prepare_latents_ddim_inverted(image, batch_size, num_images_per_prompt, text_embeddings, store_attention=False,
-                                                         generator=generator)[-1]
+            # the internal inversion runs batch 1 through the UNet: the edit controller registered by p2preplace_edit must not see it
+            # (the reference's inversion hooks run the store logic of the edit controller on that pass; here it is detached)
+            registered = getattr(self.unet, "_controller", None)
+            attention_util.register_attention_control(self, self.empty_controller)
+            try:
+                latents = self.prepare_latents_ddim_inverted(image, batch_size, num_images_per_prompt, text_embeddings,
+                                                             store_attention=False, generator=generator)[-1]
+            finally:
+                attention_util.register_attention_control(self, registered)
         latents_dtype = latents.dtype
         x = latents.detach().to(self.unet.device, torch.float32).contiguous().clone()
         text_embeddings = text_embeddings.contiguous()

@@ -268,7 +268,11 @@ class UNetPseudo3DConditionModel(nn.Module):
             raise RuntimeError("fatezero_b200.UNetPseudo3DConditionModel runs on CUDA (sm_100a) only; move the model and inputs to "
                                "the GPU — there is no CPU fallback")
         t = float(timestep.item()) if torch.is_tensor(timestep) else float(timestep)
-        eps = self.engine().forward(sample, t, encoder_hidden_states, self._controller)
+        if sample.device != self.device:
+            raise RuntimeError(f"sample lives on {sample.device} but the UNet parameters on {self.device}")
+        # every launch, workspace and controller slab of the forward belongs to the UNet's device, whatever the caller's current device is
+        with torch.cuda.device(self.device):
+            eps = self.engine().forward(sample, t, encoder_hidden_states, self._controller)
         eps = eps.to(sample.dtype) if sample.dtype != torch.float32 else eps
         if not return_dict:
             return (eps,)

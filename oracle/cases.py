@@ -40,5 +40,23 @@ CASES = {
         frames=2, size=32, steps=3, source="a silver jeep driving down a curvy road", target="a silver tank driving down a curvy road",
         p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.6,
                  eq_params={"words": ["silver", "tank"], "values": [2.0, 4.0]})),
+    # ---- SD-1.4 geometry (head dims 40/80/160): too slow for the CPU oracle inside the suites, so these goldens are compared with
+    # the CUDA product directly (tests/test_gpu_golden_sd14.py); big=True -> make_golden keeps map slices + checksums only ----
+    # BASELINE config #1: config/low_resource_teaser/jeep_watercolor_ddim_10_steps.yaml (Refine + Reweight x10, ['mid'] / 640)
+    "sd14_config1": dict(
+        gpu=False, big=True, unet="sd14", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=640),
+        frames=8, size=64, steps=10, source=SRC, target="watercolor painting of " + SRC,
+        p2p=dict(is_replace_controller=False, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.8,
+                 eq_params={"words": ["watercolor"], "values": [10, 10]})),
+    # BASELINE config #3 semantics at SD-1.4 geometry: Replace + self-attention mask blend + latent blend
+    # (config/attribute/bear_tiger_lion_leopard.yaml:65-69 + config/teaser/jeep_posche_local_latent_blend.yaml:29-39)
+    "sd14_replace_blend": dict(
+        gpu=False, big=True, unet="sd14", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=640),
+        frames=2, size=64, steps=4, source=SRC, target="a Porsche car driving down a curvy road in the countryside",
+        p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.7}, self_replace_steps=0.7,
+                 blend_words=[["silver", "jeep"], ["Porsche", "car"]], blend_self_attention=True, blend_latents=True,
+                 blend_th=[0.985, 0.985])),
 }
 GPU_CASES = [k for k, v in CASES.items() if v.get("gpu", True)]
+BIG_CASES = [k for k, v in CASES.items() if v.get("big")]
+SMALL_CASES = [k for k, v in CASES.items() if not v.get("big")]
