@@ -158,11 +158,14 @@ def instrument_tapgemm(pipe, x0_dev, emb_src):
 
     saved = (ops.gemm, ops.conv3x3, ops.tconv3)
     ops.gemm, ops.conv3x3, ops.tconv3 = wrap(ops.gemm, gemm_flops), wrap(ops.conv3x3, conv_flops), wrap(ops.tconv3, tconv_flops)
+    mode = pipe.graph_mode
+    pipe.graph_mode = "off"  # the instrumented pass needs the Python-level launches (a graph replay does not pass through ops.*)
     try:
         edit_clip(pipe, x0_dev, emb_src)
         torch.cuda.synchronize()
     finally:
         ops.gemm, ops.conv3x3, ops.tconv3 = saved
+        pipe.graph_mode = mode
     flops = sum(r[0] for r in rec)
     secs = sum(r[1].elapsed_time(r[2]) for r in rec) / 1e3
     if os.environ.get("FZ_SHAPE_REPORT"):

@@ -38,6 +38,12 @@ class AttnArgs(C.Structure):
     ]
 
 
+class P2PSeg(C.Structure):
+    """fz_p2p_seg_t"""
+    _fields_ = [("src", c_void_p), ("src_pitch", c_ll), ("dst", c_void_p), ("dst_pitch", c_ll), ("rows", c_int), ("row_bytes", c_int),
+                ("dst_slot", c_int)]
+
+
 EPI_ROWMAJOR, EPI_GEGLU = 0, 1
 ATTN_NONE, ATTN_STORE, ATTN_REPLACE, ATTN_BLEND, ATTN_CROSSEDIT = 0, 1, 2, 3, 4
 XEDIT_FLOATS = 8 + 4 * 80 + 80 * 80
@@ -48,6 +54,7 @@ SIGNATURES = {
     "fz_conv3x3_nhwc_f16": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, C.POINTER(Epilogue), c_void_p, c_ll,
                             c_int, c_void_p],
     "fz_tconv3_f16": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(Epilogue), c_void_p, c_ll, c_int, c_void_p],
+    "fz_tconv3_halo_f16": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, C.POINTER(Epilogue), c_void_p, c_ll, c_int, c_void_p],
     "fz_attention_f16": [C.POINTER(AttnArgs), c_void_p],
     "fz_groupnorm_nhwc_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p,
                               c_void_p],
@@ -67,14 +74,24 @@ SIGNATURES = {
     "fz_cfg_ddim_step": [c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "fz_blend_mask": [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), c_float, c_int, c_int,
                       c_void_p, c_void_p],
+    "fz_p2p_alloc": [c_ll, C.POINTER(c_void_p)],
+    "fz_p2p_free": [c_void_p],
+    "fz_p2p_export": [c_void_p, c_void_p],
+    "fz_p2p_import": [c_void_p, C.POINTER(c_void_p)],
+    "fz_p2p_unimport": [c_void_p],
+    "fz_p2p_push": [C.POINTER(P2PSeg), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_void_p],
+    "fz_p2p_wait": [c_void_p, C.c_uint, c_void_p],
+    "fz_gn_combine": [c_void_p, C.c_uint, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "fz_device_check": [],
+    "fz_init": [c_void_p],
     "fz_version": [],
 }
 
 _lib = None
 launch_count = 0     # C-ABI compute calls issued
 kernel_launches = 0  # kernels of this library launched (bench.py reports the delta over its timed region)
-KERNELS_PER_CALL = {"fz_groupnorm_nhwc_f16": 2}  # stats + apply (plus one memset); every other entry point launches one kernel
+KERNELS_PER_CALL = {"fz_groupnorm_nhwc_f16": 2, "fz_p2p_alloc": 0, "fz_p2p_free": 0, "fz_p2p_export": 0, "fz_p2p_import": 0,
+                    "fz_p2p_unimport": 0, "fz_init": 0}  # stats + apply (plus one memset); every other entry point launches one kernel
 
 
 def load():

@@ -109,6 +109,7 @@ class AttentionStore(AttentionControl):
         self.attention_store_all_step: List[Dict[str, List[torch.Tensor]]] = []
         self.attention_store_paths: List[str] = []
         self._pos = {k: 0 for k in KEYS}
+        self._graph_plan_id = None  # set when the maps live in the memory pool of a captured inversion plan (graphs.py)
 
     @staticmethod
     def get_empty_store():
@@ -203,6 +204,31 @@ class AttentionStore(AttentionControl):
         store = self.attention_store
         return {key: [item / self.cur_step for item in store[key]] for key in store}
 
+    # ---- CUDA-graph replay support (graphs.py): the launch sequence of a loop depends on the controller only through this signature;
+    # after a replay the captured controller's end-of-loop state (same slabs, refilled) is adopted by the caller's controller object ----
+    _ADOPT = ("cur_step", "cur_att_layer", "step_store", "_acc", "_self_sum_cache", "latents_store", "attention_store_all_step",
+              "attention_store_paths", "_pos")
+
+    def graph_signature(self):
+        if type(self) is not AttentionStore or self.disk_store:
+            return None
+        return ("store", bool(self.save_self_attention), bool(self.LOW_RESOURCE))
+
+    def is_pristine(self) -> bool:
+        return self.cur_step == 0 and not self.attention_store_all_step and not self.latents_store and not self._acc
+
+    def adopt_from(self, tmpl: "AttentionStore"):
+        if tmpl is self:
+            return
+        for k in self._ADOPT:
+            v = getattr(tmpl, k)
+            if isinstance(v, list):
+                v = list(v)
+            elif isinstance(v, dict):
+                v = {kk: (list(vv) if isinstance(vv, list) else vv) for kk, vv in v.items()}
+            setattr(self, k, v)
+        self._graph_plan_id = getattr(tmpl, "_graph_plan_id", None)
+
     def reset(self):
         super().reset()
         self.step_store = self.get_empty_store()
@@ -240,6 +266,7 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         self.use_inversion_attention = use_inversion_attention
         self.attention_position_counter_dict = {k: 0 for k in KEYS}
         self._xedit = None
+        self._graph_plan_id = None
         self._mask_cache: Dict[Tuple[int, int], torch.Tensor] = {}
         if save_self_attention:
             warnings.warn("AttentionControlEdit(save_self_attention=True): pre-edit self-attention maps of the edit pass are not "
@@ -269,6 +296,49 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
             mm[:77, :77] = M.reshape(77, 77)
             tab[:, 328:] = mm.reshape(-1)
         return tab.to(device).contiguous()
+
+    def prepare_tables(self, device):
+        """Build the device-side edit tables now (a graph capture must not contain the pageable host-to-device copy)."""
+        if self._xedit is None:
+            self._xedit = self._build_xedit(device)
+
+    def load_tables_from(self, other: "AttentionControlEdit"):
+        """Refresh this (captured) controller's device tables with the content of `other` (same structure, new prompts)."""
+        self.prepare_tables(other._xedit.device if other._xedit is not None else self._xedit.device)
+        if other is not self:
+            self._xedit.copy_(other._build_xedit("cpu"), non_blocking=False)
+
+    _ADOPT_EDIT = AttentionStore._ADOPT + ("attention_position_counter_dict", "_mask_cache", "_xedit")
+
+    def graph_signature(self):
+        """Everything that shapes the launch sequence of the edit loop (table CONTENT is refreshed per replay, see load_tables_from)."""
+        if self.disk_store or self.additional_attention_store is None:
+            return None
+
+        def blender(b):
+            if b is None:
+                return None
+            return (b.prompt_choose, tuple(float(t) for t in b.th), b.start_blend, b.end_blend,
+                    tuple(b.alpha_layers.reshape(-1).tolist()))
+        return ("edit", self.num_steps, tuple(self.num_self_replace), bool(self.use_inversion_attention), bool(self.LOW_RESOURCE),
+                blender(self.latent_blend), blender(self.attention_blend),
+                getattr(self.additional_attention_store, "_graph_plan_id", None))
+
+    def adopt_from(self, tmpl: "AttentionControlEdit"):
+        if tmpl is self:
+            return
+        for k in self._ADOPT_EDIT:
+            v = getattr(tmpl, k)
+            if isinstance(v, list):
+                v = list(v)
+            elif isinstance(v, dict):
+                v = {kk: (list(vv) if isinstance(vv, list) else vv) for kk, vv in v.items()}
+            setattr(self, k, v)
+        for name in ("latent_blend", "attention_blend"):
+            mine, theirs = getattr(self, name), getattr(tmpl, name)
+            if mine is not None and theirs is not None:
+                mine.counter = theirs.counter
+                mine.mask_list = list(theirs.mask_list)
 
     def _step_in_store(self) -> int:
         if self.use_inversion_attention:
@@ -468,6 +538,9 @@ def register_attention_control(model, controller):
         raise TypeError("register_attention_control needs a fatezero_b200 UNetPseudo3DConditionModel")
     unet.set_controller(controller)
     n = 2 * sum(1 for k in unet.state_dict() if k.endswith("attn1.to_q.weight"))
-    if controller is not None and hasattr(controller, "num_att_layers"):
-        controller.num_att_layers = n
+    if controller is not None:
+        try:
+            controller.num_att_layers = n  # attention_register.py:257 sets it on whatever object it is given
+        except AttributeError:
+            pass
     return n

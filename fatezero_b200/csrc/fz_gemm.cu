@@ -675,6 +675,26 @@ __global__ void eye_init_kernel() {
   }
 }
 
+// One-time fill of the selection table.  It synchronises the stream, which is illegal under stream capture: fz_init() runs it up front
+// (engine construction), so that the first GEMM with a skip tensor may already sit inside a CUDA-graph capture.
+static int eye_table(__half** out, cudaStream_t stream) {
+  static __half* eye = nullptr;
+  if (!eye) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    FZ_CUDA(cudaStreamIsCapturing(stream, &cs));
+    FZ_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "fz_init() must run once before the library is used under CUDA-graph capture");
+    __half* e = nullptr;
+    FZ_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&e), g_eye));
+    eye_init_kernel<<<64, 256, 0, stream>>>();
+    FZ_CUDA(cudaGetLastError());
+    // the table is read by TMA of kernels on ANY stream afterwards: make the one-time fill visible before returning
+    FZ_CUDA(cudaStreamSynchronize(stream));
+    eye = e;
+  }
+  *out = eye;
+  return FZ_OK;
+}
+
 static int fold_residuals(TapGemmParams& p, int bn, cudaStream_t stream) {
   p.n_res = 0;
   p.res_kblocks = 0;
@@ -683,14 +703,8 @@ static int fold_residuals(TapGemmParams& p, int bn, cudaStream_t stream) {
   const long long lds[2] = {p.ldr, p.ldr2};
   for (int i = 0; i < 2; ++i)
     if (rs[i] && ((reinterpret_cast<uintptr_t>(rs[i]) & 15) != 0 || lds[i] % 8 != 0)) return FZ_OK;  // not TMA-addressable: epilogue path
-  static __half* eye = nullptr;
-  if (!eye) {
-    FZ_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&eye), g_eye));
-    eye_init_kernel<<<64, 256, 0, stream>>>();
-    FZ_CUDA(cudaGetLastError());
-    // the table is read by TMA of kernels on ANY stream afterwards: make the one-time fill visible before returning
-    FZ_CUDA(cudaStreamSynchronize(stream));
-  }
+  __half* eye = nullptr;
+  if (int rc = eye_table(&eye, stream)) return rc;
   {
     uint64_t dims[3] = {64, 256, 4};
     uint64_t strides[2] = {64, 64 * 256};
@@ -773,6 +787,13 @@ extern "C" int fz_debug_gemm_counters(long long* host16) {
   FZ_CUDA(cudaDeviceSynchronize());
   FZ_CUDA(cudaMemcpyFromSymbol(host16, g_gemm_dbg, sizeof(long long) * 16));
   return FZ_OK;
+}
+
+// One-time device-side initialisation (constant tables).  Idempotent; must have run before the first call under stream capture.
+extern "C" int fz_init(cudaStream_t stream) {
+  if (int rc = check_single_device()) return rc;
+  __half* eye = nullptr;
+  return eye_table(&eye, stream);
 }
 
 // D[M,N] = A[M,K] * W[N,K]^T (+epilogue).  A, W fp16 row-major (lda, ldw in elements, multiples of 8).
@@ -872,8 +893,10 @@ extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, 
 
 // Temporal Conv1d(k=3, padding 1, no bias) over the frame axis: x [B, F, HW, Cin] fp16 (row stride ldx), w [3][Cout][Cin].
 // out[b,f,p,:] = sum_t w[t] * x[b, f+t-1, p, :]  (+ epilogue: residual = identity skip of the LoRA, group_bias = time embedding).
-extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout, const fz_epilogue_t* epi,
-                             void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+// halo = 1 (frame-sharded execution): x is [B, F+2, HW, Cin] whose frames 0 and F+1 hold the neighbour ranks' boundary frames (zeros at
+// the ends of the clip, which is what the zero padding of the un-sharded conv reads); the F output frames are the interior ones.
+static int tconv3_impl(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout, const fz_epilogue_t* epi,
+                       void* out, long long ldo, int force_block_n, int halo, cudaStream_t stream) {
   FZ_CHECK_ARG(x && w && out, "fz_tconv3: null pointer");
   FZ_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "fz_tconv3: Cin/ldx must be multiples of 8");
   int bp = std::min(HW, 128);
@@ -885,14 +908,15 @@ extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW,
   const int M = B * F * HW;
   const int rc0 = fill_epilogue(p, epi, M, Cout);
   if (rc0) return rc0;
+  const int Fx = F + 2 * halo;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)F, (uint64_t)B};
-    uint64_t strides[3] = {(uint64_t)ldx, (uint64_t)ldx * HW, (uint64_t)ldx * HW * F};
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)Fx, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)ldx, (uint64_t)ldx * HW, (uint64_t)ldx * HW * Fx};
     uint32_t box[4] = {kBlockK, (uint32_t)bp, (uint32_t)bf, 1};
     if (int rc = encode_tmap_f16(&p.tmA, x, 4, dims, strides, box, true)) return rc;
   }
   p.a_rank = 4;
-  for (int t = 0; t < 3; ++t) { p.tap_off[t][2] = t - 1; }
+  for (int t = 0; t < 3; ++t) { p.tap_off[t][2] = t - 1 + halo; }
   p.rows_per_tile = bp * bf;
   p.m_tiles = M / p.rows_per_tile;
   const int bn = pick_block_n(Cout, p.mode, force_block_n, p.m_tiles);
@@ -908,4 +932,14 @@ extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW,
   p.ndecomp = 3; p.dimsz[0] = HW; p.dimsz[1] = F; p.dimsz[2] = B;
   p.out = static_cast<__half*>(out); p.ldo = ldo;
   return dispatch_tapgemm(p, Cout, bn, stream);
+}
+
+extern "C" int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout, const fz_epilogue_t* epi,
+                             void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  return tconv3_impl(x, ldx, B, F, HW, Cin, w, Cout, epi, out, ldo, force_block_n, 0, stream);
+}
+
+extern "C" int fz_tconv3_halo_f16(const void* x_ext, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout,
+                                  const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  return tconv3_impl(x_ext, ldx, B, F, HW, Cin, w, Cout, epi, out, ldo, force_block_n, 1, stream);
 }

@@ -16,6 +16,8 @@ from typing import Dict, List, Optional
 
 import torch
 
+import ctypes as C
+
 from . import _lib, ops
 
 f16 = torch.float16
@@ -50,6 +52,9 @@ class UNetEngine:
             raise RuntimeError("UNetEngine needs the UNet parameters on a CUDA device (sm_100a); no CPU fallback exists")
         lib = _lib.load()
         _lib.check(lib.fz_device_check(), "fz_device_check")
+        with torch.cuda.device(dev):
+            _lib.check(lib.fz_init(ops._stream()), "fz_init")
+            ops._workspace(dev, 1 << 20)  # GroupNorm partial-sum workspace: allocated up front (never inside a graph capture)
         self.cfg = dict(unet.config)
         self.mc = dict(unet.model_config)
         self.dev = dev
@@ -73,30 +78,136 @@ class UNetEngine:
     # what the reference's zero-shot configs run), otherwise rejected.
     # ---------------------------------------------------------------------------------------------------------------
     def set_frame_shard(self, rank: int, world: int, group=None):
+        """The frames of ONE clip are split contiguously over `world` GPUs; this rank then calls forward() with ITS frames.  Sets up the
+        symmetric peer-memory arena (p2p.Arena; torch.distributed must be initialised — it carries the one-time IPC handle exchange)."""
         if world <= 1:
             self.shard = None
+            self.arena = None
             return
-        live = [n for n, skipped in self.lora_skip.items() if not skipped]
-        live += [n for n in self.w if n.endswith(".attn_temporal.qkv") and n[: -len(".transformer_blocks.0.attn_temporal.qkv")] + ".proj_out.bias#folded" not in self.w]
-        live += [n for n in self.w if n.endswith(".conv_temporal.weight")]
-        if live:
-            raise NotImplementedError(
-                "frame sharding needs identity temporal layers (zero LoRA-up / zero attn_temporal.to_out as produced by from_2d_model); "
-                f"{len(live)} temporal layers carry weights (first: {live[0]}): halo / all-to-all exchange for them is not built yet")
+        from . import p2p
         self.shard = (int(rank), int(world), group)
+        if getattr(self, "arena", None) is None or self.arena.world != world or self.arena.rank != rank:
+            self.arena = p2p.Arena(int(rank), int(world), self.dev, group)
 
-    def _gn_joint(self, x3: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, F: int, silu: bool) -> torch.Tensor:
-        """nn.GroupNorm over (C/G, F_total, H, W) (resnet.py:338,369; unet_3d_condition.py:439) with the frames of other ranks included."""
+    def shard_signature(self):
+        """Part of the CUDA-graph plan keys (graphs.py): a frame-sharded forward launches a different kernel sequence."""
+        return None if self.shard is None else (self.shard[0], self.shard[1])
+
+    # ---- exchange helpers (all of them: fz_p2p_push into the peers' site buffers, then a wait kernel on the local flags) -------------
+    def _gn_joint(self, name: str, x3: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, F: int, silu: bool) -> torch.Tensor:
+        """nn.GroupNorm over (C/G, F_total, H, W) (resnet.py:338,369; unet_3d_condition.py:439) with the frames of other ranks included:
+        every rank pushes its per-image (sum, sumsq) [NB, G] into each peer's inbox (512 B .. 2 KiB over NVLink), fz_gn_combine waits for the
+        peers and folds everything into the layout the apply kernel reads."""
         if self.shard is None:
             return ops.groupnorm(x3, gamma, beta, eps, self.groups, F, silu)
+        rank, world, _ = self.shard
+        ar = self.arena
+        NB, G = x3.shape[0], self.groups
+        nb = NB * G * 8
+        sums = ops.groupnorm_stats(x3, G)                                  # [NB, G, 2] fp32 view into the workspace
+        site = ar.site(("gn", name, NB), world * nb)
+        st = ops._stream()
+        ar.push(site, [(sums.data_ptr(), nb, r, ar.peer_ptr(r, site, rank * nb), nb, 1, nb) for r in range(world) if r != rank], st)
+        _lib.call("fz_gn_combine", C.c_void_p(ar.base + site.flag_offset), ar.wait_mask(range(world)), C.c_void_p(ar.base + site.offset),
+                  C.c_void_p(sums.data_ptr()), NB, F, G, world, rank, st)
+        return ops.groupnorm_apply(x3, gamma, beta, eps, G, F, F * world, silu, sums)
+
+    def _halo_ext(self, key: tuple, y4: torch.Tensor) -> torch.Tensor:
+        """y4 [B, F, HW, C] (this rank's frames) -> [B, F+2, HW, C] in the arena: interior = y4, frame 0 / F+1 = the last / first frame of the
+        left / right neighbour rank (zeros at the clip ends: the zero padding of the un-sharded Conv1d, resnet.py:72-78)."""
+        rank, world, _ = self.shard
+        ar = self.arena
+        B, F, HW, Cc = y4.shape
+        fb = HW * Cc * 2
+        site = ar.site(key + (B, F, HW, Cc), B * (F + 2) * fb)
+        src = y4.data_ptr()
+        segs = [(src, F * fb, rank, ar.peer_ptr(rank, site, fb), (F + 2) * fb, B, F * fb)]
+        srcs = []
+        if rank > 0:
+            segs.append((src, F * fb, rank - 1, ar.peer_ptr(rank - 1, site, (F + 1) * fb), (F + 2) * fb, B, fb))
+            srcs.append(rank - 1)
+        if rank < world - 1:
+            segs.append((src + (F - 1) * fb, F * fb, rank + 1, ar.peer_ptr(rank + 1, site, 0), (F + 2) * fb, B, fb))
+            srcs.append(rank + 1)
+        st = ops._stream()
+        ar.push(site, segs, st)
+        ar.wait(site, srcs, st)
+        return ar.tensor(site, 0, (B, F + 2, HW, Cc))
+
+    def _temporal_attn_sharded(self, name: str, qkvt: torch.Tensor, B: int, F: int, S: int, heads: int, d: int, scale: float) -> torch.Tensor:
+        """Temporal attention over ALL frames of the clip (models/attention.py:327-337) as a frames<->pixels exchange: rank q receives the
+        q-th pixel slice of every frame's q|k|v, attends over the whole frame axis for those pixels and returns the outputs to the frames'
+        owners (3.5 C values per token over NVLink at 8 GPUs instead of the 14 C of a K/V all-gather)."""
+        rank, world, _ = self.shard
+        ar = self.arena
+        Cc = heads * d
+        if S % world:
+            raise NotImplementedError(f"frame sharding: {S} pixels do not split over {world} ranks")
+        Ss, Ft = S // world, F * world
+        st = ops._stream()
+        row_in = Ss * 3 * Cc * 2
+        site_in = ar.site(("ta_in", name, B, F, S, Cc), B * Ft * row_in)
+        q0 = qkvt.data_ptr()
+        segs = [(q0 + (b * F * S + r * Ss) * 3 * Cc * 2, S * 3 * Cc * 2, r, ar.peer_ptr(r, site_in, (b * Ft + rank * F) * row_in), row_in, F, row_in)
+                for r in range(world) for b in range(B)]
+        ar.push(site_in, segs, st)
+        ar.wait(site_in, range(world), st)
+        buf = ar.tensor(site_in, 0, (B * Ft * Ss, 3 * Cc))
+        os_ = ops.temporal_attn(buf, B, Ft, Ss, heads, d, scale)             # [B * Ft * Ss, C]
+        row_out = Ss * Cc * 2
+        site_out = ar.site(("ta_out", name, B, F, S, Cc), B * F * S * Cc * 2)
+        o0 = os_.data_ptr()
+        segs = [(o0 + (b * Ft + r * F) * row_out, row_out, r, ar.peer_ptr(r, site_out, (b * F * S + rank * Ss) * Cc * 2), S * Cc * 2, F, row_out)
+                for r in range(world) for b in range(B)]
+        ar.push(site_out, segs, st)
+        ar.wait(site_out, range(world), st)
+        return ar.tensor(site_out, 0, (B * F * S, Cc))
+
+    def _kv_exchange(self, name: str, qk: torch.Tensor, vt: torch.Tensor, index_list, B: int, F: int, S: int, Cc: int, heads: int, d: int):
+        """K and V^T of the frames the sparse-causal attention reads (attention_register.py:162-193).  Constant source frames ('first',
+        'mid', 'last': the reference's zero-shot configs) are pushed by their owner to every rank (1/F_total of an all-gather); relative
+        indices take the all-gather over the frame axis.  Returns (k_src, vt_src, n_src, src_index)."""
         from . import dist as fzdist
-        _, world, group = self.shard
-        NB = x3.shape[0]
-        sums = ops.groupnorm_stats(x3, self.groups)                       # [NB, G, 2] fp32 view into the workspace
-        set_sums = fzdist.allreduce_set_sums(sums, F, group)              # [B, G, 2] over all ranks
-        sums.zero_()
-        sums.view(NB // F, F, self.groups, 2)[:, 0] = set_sums            # the apply kernel adds the F slots of a set
-        return ops.groupnorm_apply(x3, gamma, beta, eps, self.groups, F, F * world, silu, sums)
+        rank, world, _ = self.shard
+        ar = self.arena
+        st = ops._stream()
+        fis = sc_frame_indices(index_list, F * world)  # indices over the GLOBAL frames; rank r holds [r*F, (r+1)*F)
+        kb, vb = S * Cc * 2, heads * d * S * 2         # bytes of one frame's K rows / V^T block
+        q0, v0 = qk.data_ptr(), vt.data_ptr()
+        ld = qk.stride(0) * 2
+        if all(isinstance(ix, str) for ix in index_list):
+            n = len(fis)
+            site = ar.site(("kv_const", name, B, F, S, Cc, n), n * B * (kb + vb))
+            voff = n * B * kb
+            # all slots this rank owns travel in ONE push, so that every owner raises its flag exactly once per exchange
+            segs = []
+            for sl, fi in enumerate(fis):
+                owner, gl = fi[0] // F, fi[0] % F
+                if owner == rank:
+                    for r in range(world):
+                        for b in range(B):
+                            segs.append((q0 + (b * F + gl) * S * ld + Cc * 2, ld, r, ar.peer_ptr(r, site, (sl * B + b) * kb), Cc * 2, S, Cc * 2))
+                            segs.append((v0 + (b * F + gl) * vb, vb, r, ar.peer_ptr(r, site, voff + (sl * B + b) * vb), vb, 1, vb))
+            if segs:
+                ar.push(site, segs, st)
+            ar.wait(site, sorted({fi[0] // F for fi in fis}), st)
+            k_src = ar.tensor(site, 0, (n * B * S, Cc))
+            vt_src = ar.tensor(site, voff, (n * B, heads, d, S))
+            src_index = [[sl * B + b for b in range(B) for _ in range(F)] for sl in range(n)]
+            return k_src, vt_src, n * B, src_index
+        NB = B * F
+        site = ar.site(("kv_all", name, B, F, S, Cc), world * NB * (kb + vb))
+        voff = world * NB * kb
+        segs = []
+        for r in range(world):
+            segs.append((q0 + Cc * 2, ld, r, ar.peer_ptr(r, site, rank * NB * kb), Cc * 2, NB * S, Cc * 2))
+            segs.append((v0, NB * vb, r, ar.peer_ptr(r, site, voff + rank * NB * vb), NB * vb, 1, NB * vb))
+        ar.push(site, segs, st)
+        ar.wait(site, range(world), st)
+        k_src = ar.tensor(site, 0, (world * NB * S, Cc))
+        vt_src = ar.tensor(site, voff, (world * NB, heads, d, S))
+        src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
+        return k_src, vt_src, world * NB, src_index
 
     # ---------------------------------------------------------------------------------------------------------------
     # weight packing
@@ -217,13 +328,15 @@ class UNetEngine:
         NB, H, W, C = y.shape
         M = NB * H * W
         y4 = y.view(B, F, H * W, C)
+        sh = self.shard is not None
         if name + ".conv_temporal.down.weight" in w:
-            mid = ops.tconv3(y4, w[name + ".conv_temporal.down.weight"])
-            out = ops.tconv3(mid, w[name + ".conv_temporal.up.weight"], residual=y4, residual2=residual2, group_bias=group_bias,
-                             rows_per_group=M)
+            # frame-sharded: the Conv1d pair needs one boundary frame of the neighbour ranks for each conv (y, then the rank-160 intermediate)
+            mid = ops.tconv3(self._halo_ext(("halo_y", name), y4) if sh else y4, w[name + ".conv_temporal.down.weight"], halo=sh)
+            out = ops.tconv3(self._halo_ext(("halo_mid", name), mid) if sh else mid, w[name + ".conv_temporal.up.weight"], residual=y4,
+                             residual2=residual2, group_bias=group_bias, rows_per_group=M, halo=sh)
         else:
-            out = ops.tconv3(y4, w[name + ".conv_temporal.weight"], bias=w[name + ".conv_temporal.bias"], residual2=residual2,
-                             group_bias=group_bias, rows_per_group=M)
+            out = ops.tconv3(self._halo_ext(("halo_y", name), y4) if sh else y4, w[name + ".conv_temporal.weight"],
+                             bias=w[name + ".conv_temporal.bias"], residual2=residual2, group_bias=group_bias, rows_per_group=M, halo=sh)
         return out.view(NB, H, W, C)
 
     def _has_temporal(self, name: str) -> bool:
@@ -245,12 +358,12 @@ class UNetEngine:
         """ResnetBlockPseudo3D.forward (resnet.py:335-394)."""
         w = self.w
         NB, H, W, Cin = x.shape
-        n1 = self._gn_joint(x.view(NB, H * W, Cin), w[p + ".norm1.weight"], w[p + ".norm1.bias"], self.eps, F, True)
+        n1 = self._gn_joint(p + ".norm1", x.view(NB, H * W, Cin), w[p + ".norm1.weight"], w[p + ".norm1.bias"], self.eps, F, True)
         a, b = self.temb_slices[p]
         tb = temb_all[a:b].view(1, b - a)
         h = self.conv(p + ".conv1", n1.view(NB, H, W, Cin), B, F, group_bias=tb)
         Cout = h.shape[-1]
-        n2 = self._gn_joint(h.view(NB, H * W, Cout), w[p + ".norm2.weight"], w[p + ".norm2.bias"], self.eps, F, True)
+        n2 = self._gn_joint(p + ".norm2", h.view(NB, H * W, Cout), w[p + ".norm2.weight"], w[p + ".norm2.bias"], self.eps, F, True)
         if p + ".conv_shortcut.weight" in w:
             sc = ops.gemm(x.view(-1, Cin), w[p + ".conv_shortcut.weight"], bias=w[p + ".conv_shortcut.bias"]).view(NB, H, W, Cout)
         else:
@@ -282,36 +395,7 @@ class UNetEngine:
         qk = ops.gemm(ln1, w[bp + ".attn1.qkv"], vt=dict(out=vt, col_start=2 * C, S=S, d=d, heads=heads))
         k_src, vt_src, n_src = qk[:, C:], vt, NB
         if self.shard is not None and index_list:
-            # K / V^T of every frame of the clip: NCCL all-gather over the frame axis (attention_register.py:162-193 indexes the whole clip)
-            import torch.distributed as dist
-            from . import dist as fzdist
-            rank, world, group = self.shard
-            fis = sc_frame_indices(index_list, F * world)  # indices over the GLOBAL frames; rank r holds [r*F, (r+1)*F)
-            if all(isinstance(ix, str) for ix in index_list):
-                # 'first' / 'mid' / 'last': every query frame reads the SAME source frame -> broadcast that one frame's K / V^T from its
-                # owner (1/F_total of the all-gather bytes); slot s of the source buffer holds [B] frames
-                k_src = torch.empty((len(fis) * B * S, C), dtype=f16, device=self.dev)
-                vt_src = torch.empty((len(fis) * B, heads, d, S), dtype=f16, device=self.dev)
-                for sl, fi in enumerate(fis):
-                    owner, gl = fi[0] // F, fi[0] % F
-                    kb, vb = k_src[sl * B * S:(sl + 1) * B * S], vt_src[sl * B:(sl + 1) * B]
-                    if owner == rank:
-                        kb.view(B, S, C).copy_(qk.view(B, F, S, qk.shape[1])[:, gl, :, C:2 * C])
-                        vb.copy_(vt.view(B, F, heads, d, S)[:, gl])
-                    src = dist.get_global_rank(group, owner) if group is not None else owner
-                    dist.broadcast(kb, src=src, group=group)
-                    dist.broadcast(vb, src=src, group=group)
-                n_src = len(fis) * B
-                src_index = [[sl * B + b for b in range(B) for _ in range(F)] for sl in range(len(fis))]
-            else:
-                # relative indices (-1, +1, ...): NCCL all-gather of K and V^T over the frame axis
-                k_loc = qk[:, C:2 * C].contiguous()
-                k_src = torch.empty((world * M, C), dtype=f16, device=self.dev)
-                vt_src = torch.empty((world * NB, heads, d, S), dtype=f16, device=self.dev)
-                dist.all_gather_into_tensor(k_src, k_loc, group=group)
-                dist.all_gather_into_tensor(vt_src, vt, group=group)
-                n_src = world * NB
-                src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
+            k_src, vt_src, n_src, src_index = self._kv_exchange(p, qk, vt, index_list, B, F, S, C, heads, d)
         else:
             fis = sc_frame_indices(index_list, F) if index_list else [list(range(F))]
             src_index = [[b * F + fi[f] for b in range(B) for f in range(F)] for fi in fis]
@@ -353,7 +437,10 @@ class UNetEngine:
         else:
             lnt = ops.layernorm(h, w[bp + ".norm_temporal.weight"], w[bp + ".norm_temporal.bias"])
             qkvt = ops.gemm(lnt, w[bp + ".attn_temporal.qkv"])
-            ot = ops.temporal_attn(qkvt, B, F, S, heads, d, scale)
+            if self.shard is not None:
+                ot = self._temporal_attn_sharded(p, qkvt, B, F, S, heads, d, scale)
+            else:
+                ot = ops.temporal_attn(qkvt, B, F, S, heads, d, scale)
             h = ops.gemm(ot, w[bp + ".attn_temporal.to_out.0.weight"], bias=w[bp + ".attn_temporal.to_out.0.bias"], residual=h)
         out = ops.gemm(h, w[p + ".proj_out.weight"], bias=po_bias, residual=xr)
         return out.view(NB, H, W, C)
@@ -439,7 +526,7 @@ class UNetEngine:
             if i != nblk - 1:
                 h = self.conv(f"{p}.upsamplers.0.conv", ops.upsample2x(h), B, F)
         NBh, Hh, Wh, Ch = h.shape
-        n = self._gn_joint(h.view(NB, Hh * Wh, Ch), w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.eps, F, True)
+        n = self._gn_joint("conv_norm_out", h.view(NB, Hh * Wh, Ch), w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.eps, F, True)
         co = self.cfg["out_channels"]
         # conv_out as one 16-wide MMA tile (first `co` channels valid); its bias precedes the temporal conv (resnet.py:64 then :76)
         y = ops.conv3x3(n.view(NB, Hh, Wh, Ch), w["conv_out.weight"], bias=w["conv_out.bias"])
@@ -453,4 +540,18 @@ class UNetEngine:
                 kw = dict(down=w["conv_out.conv_temporal.down.weight#f32"], up=w["conv_out.conv_temporal.up.weight#f32"])
         elif "conv_out.conv_temporal.weight" in w:
             kw = dict(w_full=w["conv_out.conv_temporal.weight#f32"], b_full=w["conv_out.conv_temporal.bias"])
-        return ops.out_temporal(y, B, co, F, H, W, **kw)
+        if self.shard is None or not kw:
+            return ops.out_temporal(y, B, co, F, H, W, **kw)
+        # frame-sharded: the conv_out tail (a 4-channel Conv1d pair over frames, 2-frame reach) runs on the gathered 16-channel rows of
+        # the whole clip (131 KB per frame) and keeps this rank's frames
+        rank, world, _ = self.shard
+        ar = self.arena
+        st = ops._stream()
+        fb = H * W * 16 * 2
+        Ft = F * world
+        site = ar.site(("out_gather", B, F, H, W), B * Ft * fb)
+        segs = [(y.data_ptr(), F * fb, r, ar.peer_ptr(r, site, rank * F * fb), Ft * fb, B, F * fb) for r in range(world)]
+        ar.push(site, segs, st)
+        ar.wait(site, range(world), st)
+        full = ops.out_temporal(ar.tensor(site, 0, (B * Ft * H * W, 16)), B, co, Ft, H, W, **kw)
+        return full[:, :, rank * F:(rank + 1) * F].contiguous()

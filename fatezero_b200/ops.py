@@ -104,10 +104,13 @@ def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias=None, stride: int = 1, resid
 
 
 def tconv3(x: torch.Tensor, w3: torch.Tensor, bias=None, residual=None, group_bias=None, rows_per_group=0, force_bn: int = 0,
-           residual2=None):
-    """x [B,F,HW,Cin], w3 [3,Cout,Cin]: Conv1d(k=3,pad=1) over F -> [B,F,HW,Cout] (+bias +residual +group_bias)."""
+           residual2=None, halo: bool = False):
+    """x [B,F,HW,Cin], w3 [3,Cout,Cin]: Conv1d(k=3,pad=1) over F -> [B,F,HW,Cout] (+bias +residual +group_bias).
+    halo (frame-sharded execution): x is [B,F+2,HW,Cin] with the neighbour ranks' boundary frames in frames 0 and F+1."""
     _chk(x, f16, "tconv3"); _chk(w3, f16, "tconv3")
     B, F, HW, Cin = x.shape
+    if halo:
+        F -= 2
     Cout = w3.shape[1]
     assert x.is_contiguous() and w3.is_contiguous()
     out = torch.empty((B, F, HW, Cout), dtype=f16, device=x.device)
@@ -116,7 +119,8 @@ def tconv3(x: torch.Tensor, w3: torch.Tensor, bias=None, residual=None, group_bi
         e.ldr = residual.shape[-1]
     if residual2 is not None:
         e.ldr2 = residual2.shape[-1]
-    _lib.call("fz_tconv3_f16", _p(x), Cin, B, F, HW, Cin, _p(w3), Cout, C.byref(e), _p(out), Cout, force_bn, _stream())
+    _lib.call("fz_tconv3_halo_f16" if halo else "fz_tconv3_f16", _p(x), Cin, B, F, HW, Cin, _p(w3), Cout, C.byref(e), _p(out), Cout, force_bn,
+              _stream())
     return out
 
 

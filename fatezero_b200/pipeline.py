@@ -200,6 +200,16 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
         super().__init__(vae, text_encoder, tokenizer, unet, scheduler)
         self.store_controller = attention_util.AttentionStore(disk_store=disk_store)
         self.empty_controller = attention_util.EmptyControl()
+        # CUDA-graph execution of the two DDIM loops (graphs.py): "auto" = eager the first time a configuration is seen, captured and
+        # replayed from its second occurrence on; "off" = always eager
+        self.graph_mode = os.environ.get("FZ_GRAPHS", "auto")
+        self._plans = {}
+        self._seen = set()
+
+    def release_graphs(self):
+        """Drop every captured plan (and the HBM pools that hold their map caches)."""
+        self._plans.clear()
+        self._seen.clear()
 
     def check_inputs(self, prompt, height, width, callback_steps, strength=None):
         if not isinstance(prompt, str) and not isinstance(prompt, list):
@@ -250,24 +260,63 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
         return out
 
     @torch.no_grad()
-    def ddim_clean2noisy_loop(self, latent, text_embeddings, controller=None):
-        """p2p_ddim_spatial_temporal.py:131-148.  Returns N+1 latents (dtype of the input), [0] clean, [-1] x_T."""
+    def ddim_clean2noisy_loop(self, latent, text_embeddings, controller=None, teacher_latents=None):
+        """p2p_ddim_spatial_temporal.py:131-148.  Returns N+1 latents (dtype of the input), [0] clean, [-1] x_T.
+        teacher_latents (parity tests only): N+1 reference latents; step i then starts from teacher_latents[i] instead of this loop's
+        own x_i (and the controller stores teacher_latents[i+1]), which isolates the per-forward kernel error from its amplification
+        by the sampler."""
         weight_dtype = latent.dtype
         dev = self.unet.device
-        cond = text_embeddings.chunk(2)[1].to(dev).contiguous()
-        all_latent = [latent]
-        x = latent.detach().to(dev, torch.float32).contiguous().clone()
         ts = [int(t) for t in self.scheduler.timesteps]
         n = len(ts)
         step = self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
-        for i in range(n):
-            t = ts[n - 1 - i]
-            eps = self.unet(x, t, encoder_hidden_states=cond)["sample"]
-            a_prev = self._alpha(min(t - step, 999))
-            ops.ddim_invert_step(x, eps.contiguous(), a_prev, self._alpha(t))
-            if controller is not None:
-                controller.step_callback(x)
-            all_latent.append(x.to(dtype=weight_dtype).clone())
+        with torch.cuda.device(dev):
+            cond = text_embeddings.chunk(2)[1].to(dev).contiguous()
+
+            def inv_step(i, x, cond_, ctrl, outputs):
+                t = ts[n - 1 - i]
+                eps = self.unet(x, t, encoder_hidden_states=cond_)["sample"]
+                ops.ddim_invert_step(x, eps.contiguous(), self._alpha(min(t - step, 999)), self._alpha(t))
+                if ctrl is not None:
+                    ctrl.step_callback(x if teacher_latents is None else teacher_latents[i + 1].to(dev, torch.float32))
+                outputs.append(x.to(dtype=weight_dtype).clone())
+
+            # ---- CUDA-graph path (graphs.py): same launch sequence, captured once per configuration, no Python in the step ----
+            sig = None
+            if (self.graph_mode != "off" and teacher_latents is None and isinstance(controller, attention_util.AttentionStore)
+                    and getattr(self.unet, "_controller", None) is controller and controller.is_pristine()):
+                sig = controller.graph_signature()
+            key = None if sig is None else ("inv", tuple(latent.shape), str(weight_dtype), tuple(ts), tuple(cond.shape), sig,
+                                            id(self.unet.engine()), self.unet.engine().shard_signature())
+            if key is not None and (key in self._plans or key in self._seen):
+                plan = self._plans.get(key)
+                if plan is None:
+                    from .graphs import LoopPlan
+                    plan = LoopPlan(dev)
+                    plan.x = torch.empty(latent.shape, dtype=torch.float32, device=dev)
+                    plan.text = torch.empty_like(cond)
+                    plan.controller = controller
+                    plan.x.copy_(latent)
+                    plan.text.copy_(cond)
+                    for i in range(n):
+                        plan.steps.capture(lambda i=i: inv_step(i, plan.x, plan.text, controller, plan.outputs))
+                    controller._graph_plan_id = plan.id
+                    # the capture advanced the controller's Python state to the end of the loop; the replay below fills its tensors
+                    self._plans[key] = plan
+                plan.x.copy_(latent)
+                plan.text.copy_(cond)
+                for i in range(n):
+                    plan.steps.replay(i)
+                controller.adopt_from(plan.controller)
+                return [latent] + [o.clone() for o in plan.outputs]
+            if key is not None:
+                self._seen.add(key)
+            all_latent = [latent]
+            x = latent.detach().to(dev, torch.float32).contiguous().clone()
+            for i in range(n):
+                if teacher_latents is not None:
+                    x.copy_(teacher_latents[i].to(dev, torch.float32))
+                inv_step(i, x, cond, controller, all_latent)
         return all_latent
 
     def next_clean2noise_step(self, model_output, timestep, sample):
@@ -331,8 +380,9 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
                          negative_prompt: Optional[Union[str, List[str]]] = None, num_images_per_prompt: Optional[int] = 1,
                          eta: float = 0.0, generator=None, latents: Optional[torch.FloatTensor] = None, output_type: Optional[str] = "pil",
                          return_dict: bool = True, callback: Optional[Callable[[int, int, torch.FloatTensor], None]] = None,
-                         callback_steps: Optional[int] = 1, controller=None, **args):
-        """p2p_ddim_spatial_temporal.py:260-435 (unknown kwargs are swallowed like the reference's **args)."""
+                         callback_steps: Optional[int] = 1, controller=None, teacher_latents=None, **args):
+        """p2p_ddim_spatial_temporal.py:260-435 (unknown kwargs are swallowed like the reference's **args).
+        teacher_latents (parity tests only): reference latents AFTER each step; step i > 0 then starts from teacher_latents[i - 1]."""
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         self.check_inputs(prompt, height, width, callback_steps, strength)
@@ -357,27 +407,70 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
             finally:
                 attention_util.register_attention_control(self, registered)
         latents_dtype = latents.dtype
-        x = latents.detach().to(self.unet.device, torch.float32).contiguous().clone()
+        dev = self.unet.device
         text_embeddings = text_embeddings.contiguous()
         is_edit = isinstance(controller, attention_util.AttentionControlEdit)
         step = self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
-        for i, t in enumerate(timesteps):
+        n = len(timesteps)
+
+        def edit_step(i, x, text, ctrl):
+            t = timesteps[i]
             x2 = torch.cat([x, x], dim=0)
-            eps2 = self.unet(x2, t, encoder_hidden_states=text_embeddings).sample
-            blend = controller.latent_blend_args(x.shape[-2], x.shape[-1]) if is_edit else None
+            eps2 = self.unet(x2, t, encoder_hidden_states=text).sample
+            blend = ctrl.latent_blend_args(x.shape[-2], x.shape[-1]) if is_edit else None
             a_t, a_prev = self._alpha(t), self._alpha(t - step)
             if blend is not None:
                 ops.cfg_ddim_step(x, eps2.contiguous(), guidance_scale, a_t, a_prev, x_inv=blend["x_inv"].contiguous(),
                                   mask_a=blend["mask_a"], mask_b=blend["mask_b"], apply_blend=blend["apply_blend"])
             else:
                 ops.cfg_ddim_step(x, eps2.contiguous(), guidance_scale, a_t, a_prev)
-            if controller is not None:
+            if ctrl is not None:
                 if is_edit:
-                    controller.step_callback(x, blend_fused=True)
+                    ctrl.step_callback(x, blend_fused=True)
                 else:
-                    controller.step_callback(x)
-            if callback is not None and i % callback_steps == 0:
-                callback(i, t, x.to(latents_dtype))
+                    ctrl.step_callback(x)
+
+        with torch.cuda.device(dev):
+            sig = None
+            if (self.graph_mode != "off" and teacher_latents is None and is_edit and getattr(self.unet, "_controller", None) is controller
+                    and controller.cur_step == 0):
+                sig = controller.graph_signature()
+            key = None if sig is None else ("edit", tuple(latents.shape), tuple(timesteps), tuple(text_embeddings.shape), float(guidance_scale),
+                                            sig[:-1], id(self.unet.engine()), self.unet.engine().shard_signature())
+            store_plan = None if sig is None else sig[-1]
+            if key is not None and store_plan is not None and ((key, store_plan) in self._plans or key in self._seen):
+                plan = self._plans.get((key, store_plan))
+                if plan is None:
+                    from .graphs import LoopPlan
+                    plan = LoopPlan(dev)
+                    plan.x = torch.empty(latents.shape, dtype=torch.float32, device=dev)
+                    plan.text = torch.empty_like(text_embeddings)
+                    plan.controller = controller
+                    controller.prepare_tables(dev)
+                    plan.x.copy_(latents)
+                    plan.text.copy_(text_embeddings)
+                    for i in range(n):
+                        plan.steps.capture(lambda i=i: edit_step(i, plan.x, plan.text, controller))
+                    self._plans[(key, store_plan)] = plan
+                plan.x.copy_(latents)
+                plan.text.copy_(text_embeddings)
+                plan.controller.load_tables_from(controller)
+                for i in range(n):
+                    plan.steps.replay(i)
+                    if callback is not None and i % callback_steps == 0:
+                        callback(i, timesteps[i], plan.x.to(latents_dtype))
+                controller.adopt_from(plan.controller)
+                x = plan.x.clone()
+            else:
+                if key is not None:
+                    self._seen.add(key)
+                x = latents.detach().to(dev, torch.float32).contiguous().clone()
+                for i, t in enumerate(timesteps):
+                    if teacher_latents is not None and i > 0:
+                        x.copy_(teacher_latents[i - 1].to(x.device, torch.float32))
+                    edit_step(i, x, text_embeddings, controller)
+                    if callback is not None and i % callback_steps == 0:
+                        callback(i, t, x.to(latents_dtype))
         latents = x.to(latents_dtype)
         if output_type == "latent":
             return StableDiffusionPipelineOutput(images=latents, nsfw_content_detected=None)

@@ -25,6 +25,9 @@ const char* fz_last_error(void);
 int fz_version(void);
 /* Runtime probe: returns 0 when the current device is sm_100 and the kernels can run. */
 int fz_device_check(void);
+/* One-time device-side initialisation (constant tables; synchronises `stream` the first time).  Idempotent.  Must have run before the
+ * library is first used under CUDA-graph stream capture (fatezero_b200.engine.UNetEngine calls it at construction). */
+int fz_init(fz_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tap-GEMM family (tcgen05 / TMEM / TMA).  D[M,N] = sum_tap A_tap[M,K] W_tap[N,K]^T  (+ fused epilogue)
@@ -55,6 +58,10 @@ int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int 
 /* temporal Conv1d(k=3) of LoRALinearLayer / conv_temporal (resnet.py:72-78, lora.py:46-54) */
 int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout,
                   const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, fz_stream_t stream);
+/* same conv when the frames of the clip are sharded over GPUs: x_ext is [B, F+2, HW, Cin], frames 0 and F+1 are the neighbour ranks'
+ * boundary frames (zeros at the clip ends = the conv's zero padding), the F output frames are the interior ones */
+int fz_tconv3_halo_f16(const void* x_ext, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout,
+                       const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, fz_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused attention with the inline controller (replaces the monkeypatched closures of
@@ -140,6 +147,37 @@ int fz_cfg_ddim_step(float* x, const float* eps2, long long n, float guidance, f
 /* blend mask from cached cross maps (spatial_blend.py:24-39,78-111); maps: HOST array of device pointers, word_w: HOST [ntok] */
 int fz_blend_mask(const void* const* maps, int num_maps, int maps_f32, int F, int heads, int r, int ldm, int ntok, const float* word_w,
                   float th, int h, int w, float* out, fz_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Frame-sharded execution over the GPUs of one NVSwitch box (one process per GPU): peer-memory exchange.
+ * Replaces, for the frames-of-one-clip split of SURVEY.md §8(e), what the reference gets for free from holding every frame on one
+ * device: K / V of other frames (prompt_attention/attention_register.py:162-193), joint-frame GroupNorm statistics
+ * (models/resnet.py:338,369), the frame halo of the temporal Conv1d (models/resnet.py:72-78) and the frames<->pixels exchange of the
+ * temporal attention (models/attention.py:327-337).  A symmetric arena (fz_p2p_alloc on every rank, exported / imported with CUDA IPC)
+ * gives every rank a pointer into every peer; fz_p2p_push copies 2-D segments into peers with 16-byte NVLink stores and raises a flag in
+ * the destination's arena when all of its segments have landed; fz_p2p_wait / fz_gn_combine spin on the LOCAL flags and clear them.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* src;      /* local source (16-byte aligned) */
+  long long src_pitch;  /* bytes between source rows */
+  void* dst;            /* destination: pointer into the peer's (or the own) arena */
+  long long dst_pitch;
+  int rows;
+  int row_bytes;        /* multiple of 16 */
+  int dst_slot;         /* which flag / counter the segment reports to; -1 = local copy, no flag */
+} fz_p2p_seg_t;
+int fz_p2p_alloc(long long nbytes, void** ptr);              /* cudaMalloc + zero fill (flags start cleared) */
+int fz_p2p_free(void* ptr);
+int fz_p2p_export(void* ptr, void* handle64);                /* cudaIpcMemHandle_t, 64 bytes */
+int fz_p2p_import(const void* handle64, void** ptr);         /* peer pointer valid in this process */
+int fz_p2p_unimport(void* ptr);
+/* flags[d]: flag word in destination d's arena (peer pointer); counters[d]: local zero-initialised arrival counter */
+int fz_p2p_push(const fz_p2p_seg_t* segs, int n_segs, void* const* flags, void* const* counters, int n_dst, fz_stream_t stream);
+/* flags: local array of up to 32 flag words; waits for (and clears) those selected by mask */
+int fz_p2p_wait(void* flags, unsigned mask, fz_stream_t stream);
+/* waits like fz_p2p_wait, then adds the peers' per-image GroupNorm (sum, sumsq) (inbox [world][NB*G] float2) to sums [NB*G] float2,
+ * leaving each statistics set's total in the slot of its first local image (input layout of fz_groupnorm_apply_f16) */
+int fz_gn_combine(void* flags, unsigned mask, const void* inbox, void* sums, int NB, int F_loc, int G, int world, int me, fz_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -62,28 +62,38 @@ def run_oracle_case(case: dict, ou=None):
     return dict(inv_latents=torch.stack(inv), edit_latents=torch.stack(tr), store=store, ctrl=ctrl)
 
 
-def run_product_case(case: dict, pipe=None, device="cuda", save_path=None):
-    """Inversion + edit through the reference-facing API of the CUDA product."""
+def run_product_case(case: dict, pipe=None, device="cuda", save_path=None, teacher=None, shard=None):
+    """Inversion + edit through the reference-facing API of the CUDA product.  teacher = golden dict: every forward starts from the
+    reference's latent of that step (teacher forcing), so the returned latents carry ONE step of kernel error each."""
     import tempfile
     from fatezero_b200 import controllers
     pipe = pipe or build_product(case["unet"], case["model_config"], device)
     N = case["steps"]
     pipe.scheduler.set_timesteps(N)
     x0 = case_inputs(case).to(device)
+    frames = case["frames"]
+    if shard is not None:  # (rank, world): this process holds a contiguous block of the clip's frames (pipe.unet.set_frame_shard done by the caller)
+        from fatezero_b200 import dist as fzdist
+        x0 = fzdist.frame_slice(x0, shard[0], shard[1])
+        frames = x0.shape[2]
     emb = pipe._encode_prompt(case["source"], device, 1, True, None)
     pipe.prepare_before_train_loop()
     pipe.store_controller = controllers.AttentionStore()
     controllers.register_attention_control(pipe, pipe.store_controller)
     pipe.store_controller.LOW_RESOURCE = True
-    inv = pipe.ddim_clean2noisy_loop(x0, emb, pipe.store_controller)
+    inv = pipe.ddim_clean2noisy_loop(x0, emb, pipe.store_controller,
+                                     teacher_latents=None if teacher is None else list(teacher["inv_latents"]))
     pipe.store_controller.LOW_RESOURCE = False
     trace = []
     p = dict(case["p2p"])
+    if teacher is not None:
+        p["teacher_latents"] = list(teacher["edit_latents"])
     if p.get("blend_words") and save_path is None:
         save_path = tempfile.mkdtemp()
     h = case["size"]
     res = pipe(prompt=case["target"], source_prompt=case["source"], edit_type="swap", image=None, strength=None, generator=None,
-               num_inference_steps=N, clip_length=case["frames"], guidance_scale=7.5, num_images_per_prompt=1, latents=inv[-1],
+               num_inference_steps=N, clip_length=frames, guidance_scale=7.5, num_images_per_prompt=1,
+               latents=inv[-1] if teacher is None else teacher["inv_latents"][-1].to(device),
                uncond_embeddings_list=None, save_path=save_path, height=8 * h, width=8 * h, output_type="latent",
                callback=lambda i, t, l: trace.append(l.detach().float().cpu().clone()), use_inversion_attention=True,
                save_self_attention=False, **p)

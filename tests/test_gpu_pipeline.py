@@ -129,3 +129,54 @@ def test_sd14_single_forward(report):
             worst = max(worst, (t.float().cpu() - ostore.step_store[key][pos]).abs().max().item())
     report["sd14_forward"] = dict(rel=r, max_abs=a, maps_max_abs=worst, n_maps=sum(len(v) for v in store.step_store.values()))
     assert r < 2e-2 and worst < 3e-3
+
+
+def test_foreign_controller_slow_path(report):
+    """A controller that only speaks the reference protocol `controller(attn[BF, heads, s, t], is_cross, place) -> attn`
+    (attention_register.py:49-51) is served through the materialised-probability slow path of the engine: it sees all 32 layers,
+    the maps it sees are the ones the fused STORE mode caches, and returning them unchanged reproduces the un-hooked forward."""
+    from fatezero_b200 import controllers
+    mc = dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128)
+    pipe = build_product("mini", mc)
+    x0 = (synth.synth_latents(2, 32, 32) * 0.5).cuda()
+    emb = torch.randn(1, 77, 128, generator=torch.Generator().manual_seed(2)).cuda()
+    plain = pipe.unet(x0, 301, emb).sample
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+            self.seen = {}
+
+        def __call__(self, attn, is_cross, place):
+            self.calls.append((tuple(attn.shape), bool(is_cross), place))
+            key = f"{place}_{'cross' if is_cross else 'self'}"
+            if attn.shape[2] <= 32 ** 2:
+                self.seen.setdefault(key, []).append(attn.clone())
+            return attn
+
+    rec = Recorder()
+    controllers.register_attention_control(pipe, rec)
+    got = pipe.unet(x0, 301, emb).sample
+    assert len(rec.calls) == 32 and rec.num_att_layers == 32
+    r, a = rel(got, plain)
+    store = controllers.AttentionStore()
+    store.LOW_RESOURCE = True
+    controllers.register_attention_control(pipe, store)
+    pipe.unet(x0, 301, emb)
+    worst = 0.0
+    for key, lst in store.step_store.items():
+        assert len(lst) == len(rec.seen[key]), key
+        for t, s in zip(lst, rec.seen[key]):
+            worst = max(worst, (t.float() - s.float()).abs().max().item())
+    # an EDITING foreign controller: zero the probability of text token 1 everywhere -> output must change
+    class Editor:
+        def __call__(self, attn, is_cross, place):
+            if is_cross:
+                attn = attn.clone()
+                attn[..., 1] = 0
+            return attn
+    controllers.register_attention_control(pipe, Editor())
+    edited = pipe.unet(x0, 301, emb).sample
+    report["foreign_controller"] = dict(identity_rel=r, identity_abs=a, maps_vs_fused_store=worst, edit_delta=rel(edited, plain)[0])
+    assert r < 4e-3 and worst == 0.0  # measured 2.1e-3: un-hooked rows take the online-softmax kernel, the slow path the two-pass one
+    assert rel(edited, plain)[0] > 1e-3

@@ -1,10 +1,12 @@
-"""Frame-sharding parity: the frames of one clip over the ranks of this job versus the same clip on one GPU.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/shard_check.py
+"""Frame-sharding parity: the frames of ONE clip over the ranks of this job, with NON-identity temporal layers
+(temporal LoRA halo exchange, temporal-attention frames<->pixels exchange, K/V push, GroupNorm statistics exchange: fz_p2p.cu).
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/shard_check.py [--big]
 Checks (rank 0 prints one JSON line, exit code 1 on failure):
-  * one CFG-batch UNet forward: eps of the sharded run == eps of the single-GPU run up to the fp32 re-association of the GroupNorm sums
-  * inversion + attention-fused edit of a mini case through the reference-facing pipeline API on the rank's frames
-    (bounds: forward 4e-3, inversion 5e-3, edit 5e-2 relative; measured 1.5e-3 / 1.9e-3 / 2.1e-2 — two fp16 runs whose GroupNorm sums are associated differently; the CFG x7.5
-    sampler amplifies that like any fp16 perturbation, cf. the 1.6e-2 of the single-GPU run against the fp32 oracle)."""
+  * one CFG-batch UNet forward, sharded vs the same product on one GPU (same kernels: only the fp32 association of the GroupNorm sums and
+    the pixel split of the temporal attention differ) — bound 4e-3 of max|eps|;
+  * the committed GOLDEN cases of the unmodified reference whose frame count divides over the ranks, through the reference-facing
+    pipeline API on the rank's frames — same bounds as the single-GPU tests (tests/test_gpu_pipeline.py, tests/test_gpu_golden_sd14.py);
+  * CUDA-graph replay of the sharded loops (third run of a case) equals the eager sharded run bit for bit."""
 import json
 import os
 import sys
@@ -15,8 +17,16 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("FZ_P2P_ARENA_MB", "3072")
 from fatezero_b200 import dist as fzdist, synth  # noqa: E402
-from _helpers import build_product  # noqa: E402
+from _helpers import GOLDEN_DIR, build_product, run_product_case  # noqa: E402
+from oracle.cases import CASES  # noqa: E402
+
+
+def gmax(v: float, dev) -> float:
+    t = torch.tensor([float(v)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def main():
@@ -24,55 +34,55 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     fzdist.init("nccl", dev)
-    # FZ_SHARD_INDEX=const: only constant source frames ('mid', 'first') -> the broadcast path; default: a relative index too -> all-gather
-    index = ["mid", "first"] if os.environ.get("FZ_SHARD_INDEX") == "const" else ["mid", -1, "first"]
-    mc = dict(lora=160, SparseCausalAttention_index=index, least_sc_channel=64)
-    frames, size = 4, 32
-    pipe = build_product("mini", mc, device=dev, degenerate_temporal=True)
+    big = "--big" in sys.argv
+    out, ok = dict(world=world), True
+    # ---- (1) one forward, sharded vs single GPU, non-identity temporal layers, a relative index (all-gather path) + constant ones
+    mc = dict(lora=160, SparseCausalAttention_index=["mid", -1, "first"], least_sc_channel=64)
+    frames, size = 2 * world, 32
+    pipe = build_product("mini", mc, device=dev)
     cfg = synth.UNET_CONFIGS["mini"]
     x0 = (synth.synth_latents(frames, size, size) * 0.5).to(dev)
     x2 = torch.cat([x0, 0.7 * x0])
     emb = torch.randn(2, 77, cfg["cross_attention_dim"], generator=torch.Generator().manual_seed(2)).to(dev)
-    out = {}
-    # ---- single-GPU reference on every rank
     full = pipe.unet(x2, 481, emb).sample
-    # ---- sharded
     pipe.unet.set_frame_shard(rank, world)
     loc = pipe.unet(fzdist.frame_slice(x2, rank, world), 481, emb).sample
     got = fzdist.gather_frames(loc, world)
     pipe.unet.set_frame_shard(0, 1)
     out["forward_max_abs"] = (got - full).abs().max().item()
     out["forward_ref_max"] = full.abs().max().item()
-    # ---- pipeline: inversion + edit on the local frames
-    from fatezero_b200 import controllers
-    src, tgt = "a silver jeep driving down a curvy road", "a watercolor painting of a silver jeep driving down a curvy road"
-    p2p = dict(cross_replace_steps={"default_": 0.8}, self_replace_steps=0.7, is_replace_controller=False,
-               eq_params=dict(words=["watercolor"], values=[4.0]), blend_words=None, use_inversion_attention=True)
-    N = 4
-
-    def run(x):
-        pipe.scheduler.set_timesteps(N)
-        e = pipe._encode_prompt(src, dev, 1, True, None)
-        store = controllers.AttentionStore()
-        pipe.store_controller = store
-        controllers.register_attention_control(pipe, store)
-        store.LOW_RESOURCE = True
-        inv = pipe.ddim_clean2noisy_loop(x, e, store)
-        store.LOW_RESOURCE = False
-        o = pipe(prompt=tgt, source_prompt=src, edit_type="swap", image=None, strength=None, generator=None, num_inference_steps=N,
-                 clip_length=x.shape[2], guidance_scale=7.5, num_images_per_prompt=1, latents=inv[-1], uncond_embeddings_list=None,
-                 save_path=None, height=8 * size, width=8 * size, output_type="latent", save_self_attention=False, **p2p)
-        return inv[-1], o["sdimage_output"].images
-
-    inv_full, edit_full = run(x0)
-    pipe.unet.set_frame_shard(rank, world)
-    inv_loc, edit_loc = run(fzdist.frame_slice(x0, rank, world))
-    inv_got, edit_got = fzdist.gather_frames(inv_loc, world), fzdist.gather_frames(edit_loc, world)
-    pipe.unet.set_frame_shard(0, 1)
-    out["inv_rel"] = ((inv_got - inv_full).abs().max() / inv_full.abs().max()).item()
-    out["edit_rel"] = ((edit_got - edit_full).abs().max() / edit_full.abs().max()).item()
-    ok = out["forward_max_abs"] <= 4e-3 * max(out["forward_ref_max"], 1.0) and out["inv_rel"] <= 5e-3 and out["edit_rel"] <= 5e-2
-    out.update(world=world, frames=frames, index=index, ok=bool(ok))
+    ok &= out["forward_max_abs"] <= 4e-3 * max(out["forward_ref_max"], 1.0)
+    del pipe
+    # ---- (2) golden cases of the unmodified reference on the rank's frames (+ (3) graph replay == eager)
+    names = ["mini_replace_blend", "mini_reweight_next"] + (["sd14_replace_blend", "sd14_config1"] if big else [])
+    bounds = dict(mini_replace_blend=(2e-2, 8e-2), mini_reweight_next=(2e-2, 8e-2), sd14_replace_blend=(9.2e-3, 4.7e-2), sd14_config1=(1.2e-2, 5.5e-1))
+    for name in names:
+        case = CASES[name]
+        gpath = os.path.join(GOLDEN_DIR, f"{name}.pt")
+        if case["frames"] % world or not os.path.exists(gpath):
+            continue
+        g = torch.load(gpath)
+        blend = bool(case["p2p"].get("blend_words"))
+        pipe = build_product(case["unet"], case["model_config"], device=dev)
+        pipe.unet.set_frame_shard(rank, world)
+        runs = [run_product_case(case, pipe=pipe, device=dev, shard=(rank, world)) for _ in range(3)]  # eager, captured, replayed
+        g_inv = fzdist.frame_slice(g["inv_latents"], rank, world, dim=3)
+        g_ed = fzdist.frame_slice(g["edit_latents"], rank, world, dim=3)
+        p = runs[0]
+        d_inv = (p["inv_latents"] - g_inv).abs().max().item()
+        d = (p["edit_latents"][-1] - g_ed[-1]).abs().reshape(-1)
+        d_ed = (torch.quantile(d, 0.99) if blend else d.max()).item()
+        sharded_abs = name.startswith("sd14")
+        s_inv = 1.0 if sharded_abs else g["inv_latents"].abs().max().item()
+        s_ed = 1.0 if sharded_abs else g["edit_latents"][-1].abs().max().item()
+        e_inv, e_ed = gmax(d_inv / s_inv, dev), gmax(d_ed / s_ed, dev)
+        same = all(torch.equal(r["inv_latents"], p["inv_latents"]) and torch.equal(r["edit_latents"], p["edit_latents"]) for r in runs[1:])
+        same = gmax(0.0 if same else 1.0, dev) == 0.0
+        out[name] = dict(inv_err=e_inv, edit_err=e_ed, graph_replay_equal=same, plans=len(pipe._plans))
+        ok &= e_inv <= bounds[name][0] and e_ed <= bounds[name][1] and same and len(pipe._plans) == 2
+        del pipe, runs
+        torch.cuda.empty_cache()
+    out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.barrier()
