@@ -12,7 +12,7 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 
 
 def test_reference_arm_prints_one_json_line():
-    env = dict(os.environ, FZ_CPU_THREADS="8")
+    env = dict(os.environ, FZ_CPU_THREADS="8", FZ_REF_FRAMES="1")  # one frame instead of the clip: the contract, not the number
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -28,5 +28,5 @@ def test_reference_arm_prints_one_json_line():
 def test_bench_cli_surface():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0
-    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--shard"):
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--shard", "--config", "--graphs"):
         assert flag in r.stdout
