@@ -79,9 +79,9 @@ SIGNATURES = {
     "fz_p2p_export": [c_void_p, c_void_p],
     "fz_p2p_import": [c_void_p, C.POINTER(c_void_p)],
     "fz_p2p_unimport": [c_void_p],
-    "fz_p2p_push": [C.POINTER(P2PSeg), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_void_p],
+    "fz_p2p_push": [C.POINTER(P2PSeg), c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, C.c_uint, c_void_p],
     "fz_p2p_wait": [c_void_p, C.c_uint, c_void_p],
-    "fz_gn_combine": [c_void_p, C.c_uint, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "fz_gn_combine": [c_void_p, C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "fz_device_check": [],
     "fz_init": [c_void_p],
     "fz_version": [],

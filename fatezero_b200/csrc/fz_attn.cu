@@ -677,7 +677,13 @@ constexpr int kPlainStageBytes = 16384;
 constexpr int kPlainStages = 10;
 constexpr int kPlainSmem = 1024 + kAtomBytes + kPlainStages * kPlainStageBytes + 4096;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef FZ_POLY_SEL
+#define FZ_POLY_SEL(e) (((e) & 3) == 3)  // which exponentials of a 32-chunk take the FMA-pipe polynomial (measured optimum: 1 in 4)
+#endif
 
+// kMasked: the last key tile of a slot may be partial (77 text keys at head dims the streaming cross kernel does not take); the full-tile
+// instantiation carries no masking code at all — with it in the loop the r = 64 self-attention ran 965 us instead of 820 us (ncu).
+template <bool kMasked>
 __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -844,7 +850,7 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
       FZ_TIMED(1, mbar_wait(&s_full[b], (j / 3) & 1));
       tc_fence_after();
       const uint32_t sbase = tmem_base + lane_addr + b * 128;
-      const int tile_valid = min(128, p.keys_per_slot - ((j % tiles_per_slot) << 7));  // keys beyond it are TMA zero fill: masked to -inf
+      const int tile_valid = kMasked ? min(128, p.keys_per_slot - ((j % tiles_per_slot) << 7)) : 128;  // keys beyond it are TMA zero fill: masked to -inf
       uint32_t ra[32], rb[32];
       // ---- tile maximum (TMEM reads are cheap: the scores are read again below instead of being kept in 128 registers) ----
       {
@@ -856,10 +862,12 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
           uint32_t(&cur)[32] = (i & 1) ? rb : ra;
           uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
           if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
-          if (tile_valid < (i + 1) * 32) {
+          if constexpr (kMasked) {
+            if (tile_valid < (i + 1) * 32) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;
+              for (int e = 0; e < 32; ++e)
+                if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;
+            }
           }
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
@@ -905,16 +913,18 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
         uint32_t(&cur)[32] = (i & 1) ? rb : ra;
         uint32_t(&nxt)[32] = (i & 1) ? ra : rb;
         if (i < 3) tmem_ld_32x32b_x32(sbase + (i + 1) * 32, nxt);
-        if (tile_valid < (i + 1) * 32) {
+        if constexpr (kMasked) {
+          if (tile_valid < (i + 1) * 32) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;  // exp2(-inf) = 0 on both the MUFU and the polynomial path
+            for (int e = 0; e < 32; ++e)
+              if (i * 32 + e >= tile_valid) cur[e] = 0xff800000u;  // exp2(-inf) = 0 on both the MUFU and the polynomial path
+          }
         }
         float* pv = reinterpret_cast<float*>(cur);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const float y = fmaf(pv[e], sc2, -mb2);
-          pv[e] = ((e & 3) == 3) ? ex2_poly(y) : ex2(y);  // 3 MUFU : 1 polynomial
+          pv[e] = FZ_POLY_SEL(e) ? ex2_poly(y) : ex2(y);  // 3 MUFU : 1 polynomial
         }
 #pragma unroll
         for (int e = 0; e < 32; e += 4) { lf0 += pv[e]; lf1 += pv[e + 1]; lf2 += pv[e + 2]; lf3 += pv[e + 3]; }
@@ -980,6 +990,229 @@ __global__ void __launch_bounds__(320, 1) attn_plain_kernel(const __grid_constan
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hook-free text cross-attention at the 64x64-latent layers (attention_register.py:71-128 with q.shape[1] > 32**2: 77 keys, head dim 40).
+// 0.4 % of the FLOPs, but one CTA per 128 queries through the generic pipeline is a ~5 us dependent chain (Q load -> QK^T -> softmax ->
+// PV -> store) with one CTA per SM: 143 us per launch at BF = 16 against 13 us of HBM time (ncu, profiles/r02_shapes_v0.json).
+// Here a CTA keeps K (one atom) and V^T (two atoms) of its (frame, head) in shared memory and STREAMS a range of query tiles through a
+// two-deep pipeline: Q tiles arrive through a 2-stage TMA ring, S/P and O are double-buffered in TMEM (buffer b = 128 columns: scores /
+// packed fp16 probabilities in [0, 80), the O accumulator in [80, 128)), one warpgroup does softmax(t+1) before the epilogue of tile t, so
+// the tensor pipe, the MUFU and the global stores of consecutive tiles overlap.  256 TMEM columns and ~60 KB of shared memory: two CTAs
+// per SM.  Needs keys <= 80, d_pad <= 48, S_q % 128 == 0 (the SD-1.x r = 64 layers); everything else takes attn_plain_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCrossVAtom = 8192;  // d_pad * 128 B <= 6144, rounded to the 1024-byte swizzle-atom alignment
+constexpr int kCrossSmem = 1024 + 2 * kAtomBytes + kAtomBytes + 2 * kCrossVAtom + 512;
+
+__global__ void __launch_bounds__(192, 2) attn_cross_kernel(const __grid_constant__ AttnParams p, int tiles_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int head = blockIdx.y, bf = blockIdx.z;
+  const int q_tiles = p.S_q >> 7;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int n = min(q_tiles, t0 + tiles_per_cta) - t0;
+
+  uint8_t* s_q = smem;                       // 2 x 16 KiB
+  uint8_t* s_k = s_q + 2 * kAtomBytes;       // 128 keys x 128 B (rows >= 77 zero-filled by TMA)
+  uint8_t* s_v = s_k + kAtomBytes;           // 2 x [d_pad][64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + 2 * kCrossVAtom);
+  uint64_t* q_full = bars;        // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_full = bars + 7;    // [2]
+  uint64_t* o_full = bars + 9;    // [2]
+  uint64_t* o_free = bars + 11;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK2);
+    tma_prefetch_desc(&p.tmVt);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 4);
+      mbar_init(&o_full[b], 1);
+      mbar_init(&o_free[b], 4);
+    }
+    mbar_init(kv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int vt_atom_bytes = p.d_pad * 128;
+  const int src = p.src_index[0][bf];
+
+  if (n > 0) {
+    if (warp == 4) {
+      // =========================================== TMA producer ===========================================
+      if (elect_one()) {
+        mbar_expect_tx(kv_full, kAtomBytes + 2 * vt_atom_bytes);
+        tma_load_4d(s_k, &p.tmK2, kv_full, 0, head, 0, src);
+        tma_load_4d(s_v, &p.tmVt, kv_full, 0, 0, head, src);
+        tma_load_4d(s_v + kCrossVAtom, &p.tmVt, kv_full, 64, 0, head, src);
+        for (int i = 0; i < n; ++i) {
+          const int st = i & 1;
+          mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[st], kAtomBytes);
+          tma_load_4d(s_q + st * kAtomBytes, &p.tmQ, &q_full[st], 0, head, (t0 + i) << 7, bf);
+        }
+      }
+    } else if (warp == 5) {
+      // =========================================== MMA issuer ===========================================
+      const bool leader = elect_one();
+      const uint32_t idesc_s = umma_idesc_f16(128, 80);
+      const uint32_t idesc_o = umma_idesc_f16(128, p.d_pad);
+      const uint64_t desc_hi = umma_desc_k_sw128(0);
+      const uint32_t q_lo = (smem_u32(s_q) & 0x3FFFF) >> 4;
+      const uint32_t k_lo = (smem_u32(s_k) & 0x3FFFF) >> 4;
+      const uint32_t v_lo = (smem_u32(s_v) & 0x3FFFF) >> 4;
+      const int ksteps = (p.d + 15) >> 4;
+      auto issue_qk = [&](int i) {
+        const int b = i & 1;
+        mbar_wait(&q_full[b], (i >> 1) & 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_lo = q_lo + b * (kAtomBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ksteps) umma_f16_ss(tmem_base + b * 128, desc_hi | (a_lo + 2 * k), desc_hi | (k_lo + 2 * k), idesc_s, k ? 1u : 0u);
+          umma_commit(&q_empty[b]);
+          umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (n > 1) issue_qk(1);
+      for (int i = 0; i < n; ++i) {
+        const int b = i & 1;
+        mbar_wait(&p_full[b], (i >> 1) & 1);
+        mbar_wait(&o_free[b], ((i >> 1) & 1) ^ 1);  // the epilogue of tile i - 2 has read this O buffer
+        tc_fence_after();
+        if (leader) {
+          const uint32_t pa = tmem_base + b * 128, od = pa + 80;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const uint64_t bdesc = desc_hi | (v_lo + (k >> 2) * (kCrossVAtom >> 4) + 2 * (k & 3));
+            umma_f16_ts(od, pa + k * 8, bdesc, idesc_o, k ? 1u : 0u);
+          }
+          umma_commit(&o_full[b]);
+        }
+        __syncwarp();
+        if (i + 2 < n) issue_qk(i + 2);  // executes behind PV(i) on the tensor pipe: reuses the S/P columns PV(i) has just read
+      }
+    } else {
+      // =========================================== softmax + epilogue warpgroup ===========================================
+      const int row = warp * 32 + lane;
+      const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+      const float sc2 = p.scale_log2;
+      const int keys = p.keys_per_slot;
+      float l_sum[2] = {0.f, 0.f};
+      for (int j = 0; j <= n; ++j) {
+        if (j < n) {
+          const int b = j & 1;
+          mbar_wait(&s_full[b], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sb = tmem_base + lane_addr + b * 128;
+          uint32_t r0[32], r1[32], r2[16];
+          tmem_ld_32x32b_x32(sb, r0);
+          tmem_ld_32x32b_x32(sb + 32, r1);
+          tmem_ld_32x32b_x16(sb + 64, r2);
+          tmem_ld_wait();
+          float s[80];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { s[e] = __uint_as_float(r0[e]); s[32 + e] = __uint_as_float(r1[e]); }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) s[64 + e] = __uint_as_float(r2[e]);
+#pragma unroll
+          for (int e = 64; e < 80; ++e)
+            if (e >= keys) s[e] = -INFINITY;
+          if (keys < 64) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e)
+              if (e >= keys) s[e] = -INFINITY;
+          }
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 80; e += 4) {
+            m0 = fmaxf(m0, s[e]); m1 = fmaxf(m1, s[e + 1]); m2 = fmaxf(m2, s[e + 2]); m3 = fmaxf(m3, s[e + 3]);
+          }
+          const float mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sc2;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 80; e += 4) {
+            s[e] = ex2(fmaf(s[e], sc2, -mb)); s[e + 1] = ex2(fmaf(s[e + 1], sc2, -mb));
+            s[e + 2] = ex2(fmaf(s[e + 2], sc2, -mb)); s[e + 3] = ex2(fmaf(s[e + 3], sc2, -mb));
+            a0 += s[e]; a1 += s[e + 1]; a2 += s[e + 2]; a3 += s[e + 3];
+          }
+          l_sum[b] = (a0 + a1) + (a2 + a3);
+          uint32_t pk0[32], pk1[16];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) pk0[e] = pack_half2(s[2 * e], s[2 * e + 1]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk1[e] = pack_half2(s[64 + 2 * e], s[64 + 2 * e + 1]);
+#pragma unroll
+          for (int e = 8; e < 16; ++e) pk1[e] = 0u;
+          tmem_st_32x32b_x32(sb, pk0);
+          tmem_st_32x32b_x16(sb + 32, pk1);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[b]);
+        }
+        if (j >= 1) {
+          const int i = j - 1, b = i & 1;
+          mbar_wait(&o_full[b], (i >> 1) & 1);
+          tc_fence_after();
+          const uint32_t ob = tmem_base + lane_addr + b * 128 + 80;
+          uint32_t o0[32], o1[16];
+          tmem_ld_32x32b_x32(ob, o0);
+          tmem_ld_32x32b_x16(ob + 32, o1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[b]);
+          const float inv = 1.0f / l_sum[b];
+          __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + ((t0 + i) << 7) + row) * p.ldo + head * p.d;
+#pragma unroll
+          for (int c = 0; c < 48; c += 8) {
+            if (c < p.d) {
+              uint4 v;
+              if (c < 32) {
+                v.x = pack_half2(__uint_as_float(o0[c + 0]) * inv, __uint_as_float(o0[c + 1]) * inv);
+                v.y = pack_half2(__uint_as_float(o0[c + 2]) * inv, __uint_as_float(o0[c + 3]) * inv);
+                v.z = pack_half2(__uint_as_float(o0[c + 4]) * inv, __uint_as_float(o0[c + 5]) * inv);
+                v.w = pack_half2(__uint_as_float(o0[c + 6]) * inv, __uint_as_float(o0[c + 7]) * inv);
+              } else {
+                v.x = pack_half2(__uint_as_float(o1[c - 32 + 0]) * inv, __uint_as_float(o1[c - 32 + 1]) * inv);
+                v.y = pack_half2(__uint_as_float(o1[c - 32 + 2]) * inv, __uint_as_float(o1[c - 32 + 3]) * inv);
+                v.z = pack_half2(__uint_as_float(o1[c - 32 + 4]) * inv, __uint_as_float(o1[c - 32 + 5]) * inv);
+                v.w = pack_half2(__uint_as_float(o1[c - 32 + 6]) * inv, __uint_as_float(o1[c - 32 + 7]) * inv);
+              }
+              *reinterpret_cast<uint4*>(orow + c) = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -1049,13 +1282,30 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     uint64_t strides[3] = {(uint64_t)a->d, (uint64_t)a->ldk, (uint64_t)a->ldk * a->keys_per_slot};
     uint32_t box[4] = {64, 1, 128, 1};
     if (int rc = encode_tmap_f16(&p.tmK2, a->k, 4, dims, strides, box, true)) return rc;
+    if (a->n_slots == 1 && a->keys_per_slot <= 80 && p.d_pad <= 48) {
+      // text cross-attention of the un-hooked layers: the streaming kernel (K / V^T resident, query tiles pipelined, 2 CTAs per SM)
+      static bool configured_cross = false;
+      if (!configured_cross) {
+        FZ_CUDA(cudaFuncSetAttribute(attn_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossSmem));
+        configured_cross = true;
+      }
+      const int q_tiles = a->S_q / 128;
+      int splits = std::max(1, std::min(q_tiles, (296 + a->heads * a->BF - 1) / (a->heads * a->BF)));
+      const int tiles_per_cta = (q_tiles + splits - 1) / splits;
+      splits = (q_tiles + tiles_per_cta - 1) / tiles_per_cta;
+      FZ_CUDA(launch_pdl(attn_cross_kernel, dim3(splits, a->heads, a->BF), dim3(192), kCrossSmem, stream, p, tiles_per_cta));
+      FZ_CUDA(cudaGetLastError());
+      return FZ_OK;
+    }
     static bool configured_plain = false;
     if (!configured_plain) {
-      FZ_CUDA(cudaFuncSetAttribute(attn_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem));
+      FZ_CUDA(cudaFuncSetAttribute(attn_plain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem));
+      FZ_CUDA(cudaFuncSetAttribute(attn_plain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlainSmem));
       configured_plain = true;
     }
     dim3 grid(a->S_q / 128, a->heads, a->BF);
-    FZ_CUDA(launch_pdl(attn_plain_kernel, grid, dim3(320), kPlainSmem, stream, p));
+    if (a->keys_per_slot % 128 == 0) FZ_CUDA(launch_pdl(attn_plain_kernel<false>, grid, dim3(320), kPlainSmem, stream, p));
+    else FZ_CUDA(launch_pdl(attn_plain_kernel<true>, grid, dim3(320), kPlainSmem, stream, p));
     FZ_CUDA(cudaGetLastError());
     return FZ_OK;
   }

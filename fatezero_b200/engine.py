@@ -107,9 +107,10 @@ class UNetEngine:
         sums = ops.groupnorm_stats(x3, G)                                  # [NB, G, 2] fp32 view into the workspace
         site = ar.site(("gn", name, NB), world * nb)
         st = ops._stream()
-        ar.push(site, [(sums.data_ptr(), nb, r, ar.peer_ptr(r, site, rank * nb), nb, 1, nb) for r in range(world) if r != rank], st)
-        _lib.call("fz_gn_combine", C.c_void_p(ar.base + site.flag_offset), ar.wait_mask(range(world)), C.c_void_p(ar.base + site.offset),
-                  C.c_void_p(sums.data_ptr()), NB, F, G, world, rank, st)
+        pf = (C.c_void_p * world)(*[ar.flag_ptr(r, site, rank) if r != rank else None for r in range(world)])
+        pi = (C.c_void_p * world)(*[ar.peer_ptr(r, site, rank * nb) if r != rank else None for r in range(world)])
+        _lib.call("fz_gn_combine", C.c_void_p(ar.base + site.flag_offset), pf, pi, C.c_void_p(ar.base + site.offset), C.c_void_p(sums.data_ptr()),
+                  NB, F, G, world, rank, st)
         return ops.groupnorm_apply(x3, gamma, beta, eps, G, F, F * world, silu, sums)
 
     def _halo_ext(self, key: tuple, y4: torch.Tensor) -> torch.Tensor:
@@ -129,9 +130,7 @@ class UNetEngine:
         if rank < world - 1:
             segs.append((src + (F - 1) * fb, F * fb, rank + 1, ar.peer_ptr(rank + 1, site, 0), (F + 2) * fb, B, fb))
             srcs.append(rank + 1)
-        st = ops._stream()
-        ar.push(site, segs, st)
-        ar.wait(site, srcs, st)
+        ar.exchange(site, segs, srcs, ops._stream())
         return ar.tensor(site, 0, (B, F + 2, HW, Cc))
 
     def _temporal_attn_sharded(self, name: str, qkvt: torch.Tensor, B: int, F: int, S: int, heads: int, d: int, scale: float) -> torch.Tensor:
@@ -150,8 +149,7 @@ class UNetEngine:
         q0 = qkvt.data_ptr()
         segs = [(q0 + (b * F * S + r * Ss) * 3 * Cc * 2, S * 3 * Cc * 2, r, ar.peer_ptr(r, site_in, (b * Ft + rank * F) * row_in), row_in, F, row_in)
                 for r in range(world) for b in range(B)]
-        ar.push(site_in, segs, st)
-        ar.wait(site_in, range(world), st)
+        ar.exchange(site_in, segs, range(world), st)
         buf = ar.tensor(site_in, 0, (B * Ft * Ss, 3 * Cc))
         os_ = ops.temporal_attn(buf, B, Ft, Ss, heads, d, scale)             # [B * Ft * Ss, C]
         row_out = Ss * Cc * 2
@@ -159,8 +157,7 @@ class UNetEngine:
         o0 = os_.data_ptr()
         segs = [(o0 + (b * Ft + r * F) * row_out, row_out, r, ar.peer_ptr(r, site_out, (b * F * S + rank * Ss) * Cc * 2), S * Cc * 2, F, row_out)
                 for r in range(world) for b in range(B)]
-        ar.push(site_out, segs, st)
-        ar.wait(site_out, range(world), st)
+        ar.exchange(site_out, segs, range(world), st)
         return ar.tensor(site_out, 0, (B * F * S, Cc))
 
     def _kv_exchange(self, name: str, qk: torch.Tensor, vt: torch.Tensor, index_list, B: int, F: int, S: int, Cc: int, heads: int, d: int):
@@ -188,9 +185,7 @@ class UNetEngine:
                         for b in range(B):
                             segs.append((q0 + (b * F + gl) * S * ld + Cc * 2, ld, r, ar.peer_ptr(r, site, (sl * B + b) * kb), Cc * 2, S, Cc * 2))
                             segs.append((v0 + (b * F + gl) * vb, vb, r, ar.peer_ptr(r, site, voff + (sl * B + b) * vb), vb, 1, vb))
-            if segs:
-                ar.push(site, segs, st)
-            ar.wait(site, sorted({fi[0] // F for fi in fis}), st)
+            ar.exchange(site, segs, sorted({fi[0] // F for fi in fis}), st)
             k_src = ar.tensor(site, 0, (n * B * S, Cc))
             vt_src = ar.tensor(site, voff, (n * B, heads, d, S))
             src_index = [[sl * B + b for b in range(B) for _ in range(F)] for sl in range(n)]
@@ -202,8 +197,7 @@ class UNetEngine:
         for r in range(world):
             segs.append((q0 + Cc * 2, ld, r, ar.peer_ptr(r, site, rank * NB * kb), Cc * 2, NB * S, Cc * 2))
             segs.append((v0, NB * vb, r, ar.peer_ptr(r, site, voff + rank * NB * vb), NB * vb, 1, NB * vb))
-        ar.push(site, segs, st)
-        ar.wait(site, range(world), st)
+        ar.exchange(site, segs, range(world), st)
         k_src = ar.tensor(site, 0, (world * NB * S, Cc))
         vt_src = ar.tensor(site, voff, (world * NB, heads, d, S))
         src_index = [fzdist.gathered_source_rows(fi, rank, world, F, B) for fi in fis]
@@ -551,7 +545,6 @@ class UNetEngine:
         Ft = F * world
         site = ar.site(("out_gather", B, F, H, W), B * Ft * fb)
         segs = [(y.data_ptr(), F * fb, r, ar.peer_ptr(r, site, rank * F * fb), Ft * fb, B, F * fb) for r in range(world)]
-        ar.push(site, segs, st)
-        ar.wait(site, range(world), st)
+        ar.exchange(site, segs, range(world), st)
         full = ops.out_temporal(ar.tensor(site, 0, (B * Ft * H * W, 16)), B, co, Ft, H, W, **kw)
         return full[:, :, rank * F:(rank + 1) * F].contiguous()

@@ -105,26 +105,23 @@ class Arena:
         return self.counters.data_ptr() + 4 * idx
 
     # ---- data movement ------------------------------------------------------------------------------------------------
-    def push(self, site: Site, segs: Sequence[Tuple[int, int, int, int, int, int, int]], stream) -> None:
-        """segs: (src_ptr, src_pitch, dst_rank, dst_ptr, dst_pitch, rows, row_bytes); a flag is raised on every remote dst_rank."""
+    def exchange(self, site: Site, segs: Sequence[Tuple[int, int, int, int, int, int, int]], sources: Sequence[int], stream) -> None:
+        """ONE launch: copy segs = (src_ptr, src_pitch, dst_rank, dst_ptr, dst_pitch, rows, row_bytes) into their destination ranks, raise
+        this site's flag on every remote destination, then wait for the flags of `sources` (ranks this rank expects data from)."""
         dsts = sorted({s[2] for s in segs if s[2] != self.rank})
+        mask = self.wait_mask(sources)
+        if not segs:
+            if mask:
+                _lib.call("fz_p2p_wait", C.c_void_p(self.base + site.flag_offset), mask, stream)
+            return
         slot = {r: i for i, r in enumerate(dsts)}
         arr = (P2PSeg * len(segs))()
         for i, (src, sp, r, dst, dp, rows, rb) in enumerate(segs):
             arr[i].src, arr[i].src_pitch, arr[i].dst, arr[i].dst_pitch = src, sp, dst, dp
             arr[i].rows, arr[i].row_bytes, arr[i].dst_slot = rows, rb, slot.get(r, -1)
         flags = (C.c_void_p * max(1, len(dsts)))(*[self.flag_ptr(r, site, self.rank) for r in dsts])
-        cbase = self._counter_block(site)
-        counters = (C.c_void_p * max(1, len(dsts)))(*[cbase + 4 * i for i in range(len(dsts))])
-        _lib.call("fz_p2p_push", arr, len(segs), flags, counters, len(dsts), stream)
-
-    def wait(self, site: Site, sources: Sequence[int], stream) -> None:
-        mask = 0
-        for r in sources:
-            if r != self.rank:
-                mask |= 1 << r
-        if mask:
-            _lib.call("fz_p2p_wait", C.c_void_p(self.base + site.flag_offset), mask, stream)
+        _lib.call("fz_p2p_push", arr, len(segs), flags, C.c_void_p(self._counter_block(site)), len(dsts),
+                  C.c_void_p(self.base + site.flag_offset) if mask else None, mask, stream)
 
     def wait_mask(self, sources: Sequence[int]) -> int:
         mask = 0

@@ -171,13 +171,19 @@ int fz_p2p_free(void* ptr);
 int fz_p2p_export(void* ptr, void* handle64);                /* cudaIpcMemHandle_t, 64 bytes */
 int fz_p2p_import(const void* handle64, void** ptr);         /* peer pointer valid in this process */
 int fz_p2p_unimport(void* ptr);
-/* flags[d]: flag word in destination d's arena (peer pointer); counters[d]: local zero-initialised arrival counter */
-int fz_p2p_push(const fz_p2p_seg_t* segs, int n_segs, void* const* flags, void* const* counters, int n_dst, fz_stream_t stream);
+/* Exchange in one launch: copy the segments, raise flags[d] (flag word in destination d's arena, peer pointer) once everything has been
+ * written, then — if wait_flags is not null — wait for (and clear) this rank's own incoming flags selected by wait_mask (bit r = source
+ * rank r; wait_flags = the site's 32 local flag words).  counter: local zero-initialised arrival counter.  dst_slot of a segment is
+ * informational (-1 = local copy). */
+int fz_p2p_push(const fz_p2p_seg_t* segs, int n_segs, void* const* flags, void* counter, int n_dst, void* wait_flags, unsigned wait_mask,
+                fz_stream_t stream);
 /* flags: local array of up to 32 flag words; waits for (and clears) those selected by mask */
 int fz_p2p_wait(void* flags, unsigned mask, fz_stream_t stream);
-/* waits like fz_p2p_wait, then adds the peers' per-image GroupNorm (sum, sumsq) (inbox [world][NB*G] float2) to sums [NB*G] float2,
- * leaving each statistics set's total in the slot of its first local image (input layout of fz_groupnorm_apply_f16) */
-int fz_gn_combine(void* flags, unsigned mask, const void* inbox, void* sums, int NB, int F_loc, int G, int world, int me, fz_stream_t stream);
+/* GroupNorm statistics exchange in one launch: pushes sums [NB*G] float2 into peer_inbox[r] (rank r's inbox slot for this rank), raises
+ * peer_flags[r], waits for the peers' flags (local `flags`, one word per source), then adds the peers' statistics (inbox [world][NB*G]
+ * float2, local) to sums, leaving each statistics set's total in the slot of its first local image (input layout of fz_groupnorm_apply_f16) */
+int fz_gn_combine(void* flags, void* const* peer_flags, void* const* peer_inbox, const void* inbox, void* sums, int NB, int F_loc, int G,
+                  int world, int me, fz_stream_t stream);
 
 #ifdef __cplusplus
 }

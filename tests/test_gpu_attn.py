@@ -161,7 +161,9 @@ def make_xedit(mode, alpha, eq, a, mapper, M):
     return t.to(dev)
 
 
-@pytest.mark.parametrize("F_,S,heads,d", [(2, 64, 8, 160), (3, 256, 8, 40), (2, 1024, 8, 80), (2, 4096, 2, 40), (2, 144, 4, 16)])
+# (1, 4096, 8, 40) / (8, 4096, 8, 40): the streaming cross-attention kernel with 2 / 11 query tiles per CTA (the step's own shape)
+@pytest.mark.parametrize("F_,S,heads,d", [(2, 64, 8, 160), (3, 256, 8, 40), (2, 1024, 8, 80), (2, 4096, 2, 40), (2, 144, 4, 16),
+                                        (1, 4096, 8, 40), (8, 4096, 8, 40), (4, 1024, 8, 32)])
 def test_cross(F_, S, heads, d, report):
     B = 2
     BF = B * F_

@@ -77,7 +77,7 @@ def test_gemm_geglu(C, report):
     close(out, x * F.gelu(g), report, f"geglu_{C}", atol=2e-2, rtol=3e-3)
 
 
-@pytest.mark.parametrize("d,heads,S,BF", [(40, 8, 64, 3), (80, 8, 256, 2), (16, 4, 128, 2)])
+@pytest.mark.parametrize("d,heads,S,BF", [(40, 8, 64, 3), (80, 8, 256, 2), (16, 4, 128, 2), (40, 8, 4096, 2), (160, 8, 64, 4), (80, 8, 1024, 3)])
 def test_gemm_qkv_vt(d, heads, S, BF, report):
     C_ = d * heads
     M = BF * S

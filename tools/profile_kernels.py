@@ -26,8 +26,23 @@ def attn(S, d, mode):
     if mode == "store": return lambda: ops.attention(q, k, vt, out, **kw, row_mode=_lib.ATTN_STORE, store=cache, cache_ld=S)
     if mode == "replace": return lambda: ops.attention(q, k, vt, out, **kw, row_mode=_lib.ATTN_REPLACE, base=cache, cache_ld=S)
     return lambda: ops.attention(q, k, vt, out, **kw)
+vt_out = torch.empty(16, 8, 40, 4096, device=dev, dtype=torch.float16)
+
+
+def cross(S, d):
+    BF, heads = 16, 8
+    C_ = heads * d
+    q = torch.randn(BF * S, C_, device=dev).half(); k = torch.randn(2 * 77, C_, device=dev).half()
+    vt = torch.zeros(2, heads, d, 80, device=dev, dtype=torch.float16); vt[..., :77] = torch.randn(2, heads, d, 77, device=dev).half()
+    out = torch.empty(BF * S, C_, device=dev, dtype=torch.float16)
+    return lambda: ops.attention(q, k, vt, out, S_q=S, keys_per_slot=77, n_src=2, d=d, heads=heads, F=8, BF=BF, scale=d ** -0.5,
+                                 src_index=[[b for b in range(2) for _ in range(8)]])
+
+
+# 7) QKV linear 65536 x 960 x 320 with the V^T third written transposed (staged TMA store)   8) text cross-attention r=64 d=40 (streaming kernel)
 fns = [lambda: ops.conv3x3(x, w9), lambda: ops.gemm(a, w), lambda: ops.gemm(a, wp, bias=bp, geglu=True, force_bn=bn),
-       attn(4096, 40, "none"), attn(1024, 80, "store"), attn(1024, 80, "replace")]
+       attn(4096, 40, "none"), attn(1024, 80, "store"), attn(1024, 80, "replace"),
+       lambda: ops.gemm(a, w, vt=dict(out=vt_out, col_start=640, S=4096, d=40, heads=8)), cross(4096, 40)]
 for _ in range(2):
     for f in fns: f()
 torch.cuda.synchronize()
