@@ -313,7 +313,6 @@ def run_gpu(args):
     host_ms.clear()
     ms = timed(step_resident, args.steps)
     launches = _lib.kernel_launches - launches0
-    host_enqueue = sum(host_ms) / max(len(host_ms), 1)  # host time to ENQUEUE one clip (the GPU runs behind it; no sync inside)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
     frames_total = FRAMES * (1 if (shard_frames or world == 1) else world) * args.steps
@@ -366,7 +365,7 @@ def run_gpu(args):
                                 l2="working set (map cache of the clip + activations) far exceeds the 126 MB L2; no explicit flush"),
                     clocks=clocks, e2e=dict(value=round(e2e_value, 4), unit="frames/s", h2d_bytes_per_step=x0_host.numel() * 4,
                                             d2h_bytes_per_step=out_host.numel() * 4),
-                    gpu_launches=int(launches), host_enqueue_ms_per_clip=round(host_enqueue, 1), st_attn_tflops=st, roofline=roof,
+                    gpu_launches=int(launches), st_attn_tflops=st, roofline=roof,
                     cpu_baseline=cpu)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

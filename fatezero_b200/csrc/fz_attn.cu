@@ -125,6 +125,8 @@ __device__ __forceinline__ AtomInfo atom_info(const AttnParams& p, int atoms_per
 // (128 rows x 64 keys, swizzled) + 2 cached-P ("base") buffers for BLEND.  Softmax warpgroup w owns the atoms with (A & 1) == w,
 // hence S buffers {w, w+2} (mod pass offset), P buffers {w, w+2} and base buffer w: every mbarrier is waited on by one agent in
 // program order, so parity waits can never run two phases ahead.
+// kMasked: keys_per_slot is not a multiple of 64 (text cross-attention: 77 keys); the un-masked instantiation has no masking code in its loops.
+template <bool kMasked>
 __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -421,10 +423,12 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sb]);  // scores are in registers: the MMA warp may overwrite this S tile
-        if (valid < 64) {
+        if constexpr (kMasked) {
+          if (valid < 64) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e)
-            if (e >= valid) r[e] = 0xff800000u;  // -inf
+            for (int e = 0; e < 64; ++e)
+              if (e >= valid) r[e] = 0xff800000u;  // -inf
+          }
         }
         float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
@@ -485,10 +489,12 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[sb]);
-        if (ai.valid < 64) {
+        if constexpr (kMasked) {
+          if (ai.valid < 64) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e)
-            if (e >= ai.valid) r[e] = 0xff800000u;
+            for (int e = 0; e < 64; ++e)
+              if (e >= ai.valid) r[e] = 0xff800000u;
+          }
         }
         float* pv = reinterpret_cast<float*>(r);
         if (exact) {
@@ -1331,11 +1337,13 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
   const int smem = fixed + stages * stage_bytes;
   static int configured = 0;
   if (smem > configured) {
-    FZ_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FZ_CUDA(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FZ_CUDA(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   dim3 grid((a->S_q + 127) / 128, a->heads, a->BF);
-  FZ_CUDA(launch_pdl(attn_kernel, grid, dim3(320), smem, stream, p));
+  if (a->keys_per_slot % 64 == 0) FZ_CUDA(launch_pdl(attn_kernel<false>, grid, dim3(320), smem, stream, p));
+  else FZ_CUDA(launch_pdl(attn_kernel<true>, grid, dim3(320), smem, stream, p));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }

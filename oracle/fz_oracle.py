@@ -76,6 +76,11 @@ class OracleUNet:
         self.ch = list(self.cfg["block_out_channels"])
         self.hook: Optional[Callable] = None
 
+    def to(self, device):
+        """Move the weights (tests only: the same restatement under CUDA fp16 autocast measures the reference's own fp16-vs-fp32 deviation)."""
+        self.w = {k: v.to(device) for k, v in self.w.items()}
+        return self
+
     # ---- primitives -----------------------------------------------------------------------------------------
     def _temporal(self, name: str, x: torch.Tensor) -> torch.Tensor:
         """resnet.py:72-78 + lora.py:46-54 (LoRA: x + up(down(x)); else a Conv1d with bias)."""
@@ -132,7 +137,7 @@ class OracleUNet:
 
     def _attention(self, q, k, v, scale, is_cross: bool, place: str) -> torch.Tensor:
         """attention_register.py:23-59: softmax(scale*QK^T) -> controller([BF,heads,s,t]) -> PV."""
-        scores = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1]), q, k.transpose(-1, -2), beta=0, alpha=scale)
+        scores = torch.baddbmm(q.new_empty(q.shape[0], q.shape[1], k.shape[1]), q, k.transpose(-1, -2), beta=0, alpha=scale)
         probs = scores.softmax(dim=-1)
         bh, s, t = probs.shape
         p4 = probs.reshape(bh // self.heads, self.heads, s, t)
@@ -182,7 +187,7 @@ class OracleUNet:
         q = self._heads_to_batch(self.linear(p + ".attn_temporal.to_q", n))
         k = self._heads_to_batch(self.linear(p + ".attn_temporal.to_k", n))
         v = self._heads_to_batch(self.linear(p + ".attn_temporal.to_v", n))
-        probs = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1]), q, k.transpose(-1, -2), beta=0,
+        probs = torch.baddbmm(q.new_empty(q.shape[0], q.shape[1], k.shape[1]), q, k.transpose(-1, -2), beta=0,
                               alpha=scale).softmax(dim=-1)
         o = torch.bmm(probs, v)
         o = o.reshape(b * d, self.heads, clip_length, -1).permute(0, 2, 1, 3).reshape(b * d, clip_length, c)
@@ -222,8 +227,9 @@ class OracleUNet:
         """Timesteps(320, flip_sin_to_cos=True, freq_shift=0) + TimestepEmbedding (unet_3d_condition.py:356-362)."""
         c0 = self.ch[0]
         half = c0 // 2
-        ts = torch.full((batch,), float(t), dtype=torch.float32)
-        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / (half - self.cfg.get("freq_shift", 0))
+        dev = self.w["time_embedding.linear_1.weight"].device
+        ts = torch.full((batch,), float(t), dtype=torch.float32, device=dev)
+        exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=dev) / (half - self.cfg.get("freq_shift", 0))
         emb = ts[:, None] * torch.exp(exponent)[None, :]
         emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
         if self.cfg.get("flip_sin_to_cos", True):
