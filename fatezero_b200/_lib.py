@@ -82,6 +82,7 @@ SIGNATURES = {
     "fz_p2p_push": [C.POINTER(P2PSeg), c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, C.c_uint, c_void_p],
     "fz_p2p_wait": [c_void_p, C.c_uint, c_void_p],
     "fz_gn_combine": [c_void_p, C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "fz_cross_heatmaps": [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "fz_device_check": [],
     "fz_init": [c_void_p],
     "fz_version": [],

@@ -617,8 +617,8 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
     tc_fence_after();
     const float o_scale = (!replace && !exact) ? (1.0f / l_run) : 1.0f;
     __half* orow = p.out + (static_cast<long long>(bf) * p.S_q + min(q, p.S_q - 1)) * p.ldo + head * p.d;
-#pragma unroll 1
     const bool dual_o = p.d_pad <= 128 && n_atoms >= 2;  // odd atoms accumulated into a second O tile at +128 columns
+#pragma unroll 1
     for (int c = wg * 16; c < p.d_pad; c += 32) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_o + lane_addr + c, r);

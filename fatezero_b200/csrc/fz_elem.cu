@@ -968,3 +968,56 @@ extern "C" int fz_blend_mask(const void* const* maps, int num_maps, int maps_f32
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
+
+
+namespace fz {
+// ---------------------------------------------------------------------------------------------------------------
+// show_cross_attention on the device (prompt_attention/visualization.py:14-72): the heat map of text token `tok` in frame f is the mean
+// over the selected cross-attention maps (layers) and heads of the time-averaged probabilities, scaled to 0..255 by its own maximum.
+// The reference averages EVERY stored map (get_average_attention: self maps included) and moves the r16 cross maps to the host; here
+// one CTA per (frame, token) reads the running-sum slabs in place and emits res*res bytes — the means' constant factors cancel in v / max.
+// ---------------------------------------------------------------------------------------------------------------
+struct HeatParams {
+  const void* maps[8];
+  int num_maps, maps_f32, heads, rr, ldm, ntok;
+  unsigned char* out;  // [F, ntok, rr]
+};
+__global__ void __launch_bounds__(256) cross_heatmap_kernel(const __grid_constant__ HeatParams p) {
+  const int tok = blockIdx.x, f = blockIdx.y;
+  __shared__ float s_max[8];
+  float vmax = 0.f;
+  float vals[4];  // rr <= 1024 pixels, 256 threads
+  int nv = 0;
+  for (int px = threadIdx.x; px < p.rr; px += blockDim.x, ++nv) {
+    float a = 0.f;
+    for (int m = 0; m < p.num_maps; ++m) {
+      for (int h = 0; h < p.heads; ++h) {
+        const long long idx = ((static_cast<long long>(f) * p.heads + h) * p.rr + px) * p.ldm + tok;
+        a += p.maps_f32 ? static_cast<const float*>(p.maps[m])[idx] : __half2float(static_cast<const __half*>(p.maps[m])[idx]);
+      }
+    }
+    vals[nv] = a;
+    vmax = fmaxf(vmax, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  vmax = s_max[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) vmax = fmaxf(vmax, s_max[w]);
+  nv = 0;
+  for (int px = threadIdx.x; px < p.rr; px += blockDim.x, ++nv)
+    p.out[(static_cast<long long>(f) * p.ntok + tok) * p.rr + px] = static_cast<unsigned char>(fminf(255.f, 255.f * vals[nv] / vmax));
+}
+
+}  // namespace fz
+
+extern "C" int fz_cross_heatmaps(const void* const* maps, int num_maps, int maps_f32, int F, int heads, int res, int ldm, int ntok, unsigned char* out,
+                                 cudaStream_t stream) {
+  FZ_CHECK_ARG(maps && out && num_maps >= 1 && num_maps <= 8 && res * res <= 1024 && ntok >= 1 && ntok <= ldm, "fz_cross_heatmaps: bad args");
+  fz::HeatParams p;
+  for (int i = 0; i < 8; ++i) p.maps[i] = i < num_maps ? maps[i] : nullptr;
+  p.num_maps = num_maps; p.maps_f32 = maps_f32; p.heads = heads; p.rr = res * res; p.ldm = ldm; p.ntok = ntok; p.out = out;
+  fz::cross_heatmap_kernel<<<dim3(ntok, F), 256, 0, stream>>>(p);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}

@@ -260,6 +260,17 @@ def blend_mask(maps: Sequence[torch.Tensor], word_w: torch.Tensor, th: float, h:
     return out
 
 
+def cross_heatmaps(maps: Sequence[torch.Tensor], ntok: int) -> torch.Tensor:
+    """maps: cross-attention running sums [F, heads, r*r, ld] (fp16 or fp32) of ONE resolution -> uint8 [F, ntok, r, r] heat maps."""
+    m0 = maps[0]
+    Fm, heads, rr, _ = m0.shape
+    r = int(round(rr ** 0.5))
+    arr = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+    out = torch.empty((Fm, ntok, r, r), dtype=torch.uint8, device=m0.device)
+    _lib.call("fz_cross_heatmaps", arr, len(maps), int(m0.dtype == torch.float32), Fm, heads, r, m0.stride(2), int(ntok), _p(out), _stream())
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, S_q: int, keys_per_slot: int, n_src: int, d: int,
               heads: int, F: int, BF: int, scale: float, src_index: Sequence[Sequence[int]], edit_bf_start: int = 0,
               row_mode: int = _lib.ATTN_NONE, store=None, base=None, cache_ld: int = 0, acc=None, xedit=None, mask=None, dbg=None):

@@ -148,6 +148,12 @@ int fz_cfg_ddim_step(float* x, const float* eps2, long long n, float guidance, f
 int fz_blend_mask(const void* const* maps, int num_maps, int maps_f32, int F, int heads, int r, int ldm, int ntok, const float* word_w,
                   float th, int h, int w, float* out, fz_stream_t stream);
 
+/* show_cross_attention on the device (prompt_attention/visualization.py:14-72): out[f, tok, res*res] = 255 * a / max(a) with a = sum over the
+ * given cross-attention maps ([F, heads, res*res, ldm] fp16 or fp32 running sums) and heads of the probability of text token tok (the means'
+ * constant factors cancel).  The reference averages every stored map and copies the r16 cross maps to the host first. */
+int fz_cross_heatmaps(const void* const* maps, int num_maps, int maps_f32, int F, int heads, int res, int ldm, int ntok, unsigned char* out,
+                      fz_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Frame-sharded execution over the GPUs of one NVSwitch box (one process per GPU): peer-memory exchange.
  * Replaces, for the frames-of-one-clip split of SURVEY.md §8(e), what the reference gets for free from holding every frame on one

@@ -219,3 +219,25 @@ def test_cross(F_, S, heads, d, report):
         pe[F_:] = new
         check(out2, pv(pe, vs), report, f"cross_{name}_O_{tag}", atol=6e-3, rtol=6e-3)
         check(acc2[..., :77], cur, report, f"cross_{name}_acc_{tag}", atol=1e-3)
+
+
+def test_limits_bf64_and_over(report):
+    """The kernel's frame table holds kMaxBF = 64 (frame, batch) rows: 32 frames x CFG 2 is exactly the edge (it must work), 65 must be
+    refused with an error (never a silent truncation)."""
+    BF, F_, S, heads, d = 64, 32, 128, 2, 40
+    q, k, v, vt = make_inputs(BF, S, S, BF, heads, d, qscale=2.0)
+    si = index_list("mid", F_, BF)
+    out = torch.zeros(BF * S, heads * d, dtype=torch.float16, device=dev)
+    ops.attention(q, k, vt, out, S_q=S, keys_per_slot=S, n_src=BF, d=d, heads=heads, F=F_, BF=BF, scale=d ** -0.5, src_index=si)
+    p = ref_probs(q, k, BF, S, S, heads, d, si, d ** -0.5)
+    check(out, pv(p, gather_v(v, S, heads, d, si)), report, "self_plain_bf64", atol=4e-3, rtol=4e-3)
+    cache = torch.zeros(BF, heads, S, S, dtype=torch.float16, device=dev)
+    out2 = torch.zeros_like(out)
+    ops.attention(q, k, vt, out2, S_q=S, keys_per_slot=S, n_src=BF, d=d, heads=heads, F=F_, BF=BF, scale=d ** -0.5, src_index=si,
+                  row_mode=_lib.ATTN_STORE, store=cache, cache_ld=S)
+    check(cache, p, report, "store_bf64", atol=1.5e-3)
+    BF = 65
+    q, k, v, vt = make_inputs(BF, S, S, BF, heads, d)
+    with pytest.raises(RuntimeError, match="BF=65"):
+        ops.attention(q, k, vt, torch.zeros(BF * S, heads * d, dtype=torch.float16, device=dev), S_q=S, keys_per_slot=S, n_src=BF, d=d, heads=heads,
+                      F=65, BF=BF, scale=d ** -0.5, src_index=[list(range(BF))])

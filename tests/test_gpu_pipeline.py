@@ -180,3 +180,23 @@ def test_foreign_controller_slow_path(report):
     report["foreign_controller"] = dict(identity_rel=r, identity_abs=a, maps_vs_fused_store=worst, edit_delta=rel(edited, plain)[0])
     assert r < 4e-3 and worst == 0.0  # measured 2.1e-3: un-hooked rows take the online-softmax kernel, the slow path the two-pass one
     assert rel(edited, plain)[0] > 1e-3
+
+
+def test_device_heatmaps_match_host_path(report):
+    """show_cross_attention's per-token heat maps computed on the GPU from the running cross-attention sums (fz_cross_heatmaps) against the
+    reference's host path (get_average_attention -> aggregate over layers and heads -> 255 * a / max)."""
+    from fatezero_b200 import visualization
+    case = CASES["mini_replace_blend"]  # 64x64 latents: the five 16x16 cross maps exist
+    prod = run_product_case(case)
+    store = prod["pipe"].store_controller
+    tok = synth.ToyTokenizer()
+    n = len(tok.encode(case["source"]))
+    dev_u8 = visualization.device_heatmaps(store, 16, ["up", "down"], n)
+    assert dev_u8 is not None and dev_u8.shape == (case["frames"], n, 16, 16)
+    host = visualization.aggregate_attention([case["source"]], store, 16, ["up", "down"], True, 0)  # [F, 16, 16, 77] fp32 on the host
+    want = torch.stack([(255 * host[..., i] / host[..., i].amax(dim=(1, 2), keepdim=True)).clamp(0, 255) for i in range(n)], 1)
+    d = (dev_u8.cpu().float() - want.floor()).abs().max().item()
+    report["device_heatmaps"] = dict(max_abs_lsb=d, tokens=n)
+    assert d <= 1.0  # fp16 running sums summed in a different order: at most one grey level
+    strips = visualization.show_cross_attention(tok, case["source"], store, 16, ["up", "down"])
+    assert len(strips) == case["frames"] and strips[0].shape[1] == 256 * n
