@@ -91,12 +91,72 @@ class AttentionControl(abc.ABC):
         return None
 
 
+class HostStep:
+    """One inversion step's maps parked in PINNED host memory (host_spill mode: clips whose map cache exceeds HBM, e.g. 24 frames with
+    the default [-1, 'first'] K/V frames = 208 GiB).  The device->host copies run on a side stream behind the step that produced the maps;
+    `fetch()` brings the step back (host->device on the side stream, the consumer waits on an event), normally one step ahead of its use.
+    The reference does the equivalent with `.cpu()` + deepcopy on the critical path (attention_store.py:81-93) and `.to(device)` per layer
+    in the edit pass (attention_util.py:83-84,216-218)."""
+
+    def __init__(self, step_store: Dict[str, List[torch.Tensor]], stream: "torch.cuda.Stream"):
+        self.stream = stream
+        self.host: Dict[str, List[Tuple[torch.Tensor, int]]] = {}
+        self.dev: Optional[Dict[str, List[torch.Tensor]]] = None
+        self.ready = None
+        cur = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(cur)
+        stream.wait_event(done)
+        with torch.cuda.stream(stream):
+            for k, lst in step_store.items():
+                out = []
+                for t in lst:
+                    raw = t._base if (t._base is not None and not t.is_contiguous()) else t   # cross maps are [..., :77] views of 80-wide slabs
+                    h = torch.empty(raw.shape, dtype=raw.dtype, pin_memory=True)
+                    h.copy_(raw, non_blocking=True)
+                    raw.record_stream(stream)  # the slab may be freed by Python now: the allocator keeps it until the copy has run
+                    out.append((h, t.shape[-1]))
+                self.host[k] = out
+        self.device = cur.device if hasattr(cur, "device") else torch.device("cuda", torch.cuda.current_device())
+
+    def prefetch(self):
+        if self.dev is not None:
+            return
+        with torch.cuda.stream(self.stream):
+            dev = {}
+            for k, lst in self.host.items():
+                dev[k] = []
+                for h, width in lst:
+                    d = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+                    d.copy_(h, non_blocking=True)
+                    dev[k].append(d[..., :width] if width != h.shape[-1] else d)
+            self.ready = torch.cuda.Event()
+            self.ready.record(self.stream)
+        self.dev = dev
+
+    def fetch(self) -> Dict[str, List[torch.Tensor]]:
+        self.prefetch()
+        torch.cuda.current_stream().wait_event(self.ready)
+        for lst in self.dev.values():
+            for t in lst:
+                (t._base if t._base is not None else t).record_stream(torch.cuda.current_stream())
+        return self.dev
+
+    def release(self):
+        self.dev = None
+        self.ready = None
+
+
 class AttentionStore(AttentionControl):
     """attention_store.py:63-137 — inversion-time STORE into the HBM map cache."""
 
-    def __init__(self, save_self_attention: bool = True, disk_store: bool = False):
+    def __init__(self, save_self_attention: bool = True, disk_store: bool = False, host_spill: Optional[bool] = None):
         super().__init__()
         self.disk_store = disk_store
+        # host_spill (extension; default from $FZ_HOST_SPILL): park every finished step's maps in pinned host memory and free the HBM
+        # slabs; the edit pass prefetches them back one step ahead.  For clips whose cache does not fit HBM; forces the eager loops.
+        self.host_spill = bool(int(os.environ.get("FZ_HOST_SPILL", "0"))) if host_spill is None else bool(host_spill)
+        self._spill_stream = None
         self.store_dir = None
         if disk_store:
             self.store_dir = f"./trash/attention_cache_{time.strftime('%Y%m%d-%H%M%S')}"
@@ -172,6 +232,10 @@ class AttentionStore(AttentionControl):
             torch.save({k: [t.cpu() for t in v] for k, v in self.step_store.items()}, path)
             self.attention_store_paths.append(path)
             self.attention_store_all_step.append(path)
+        elif self.host_spill and any(len(v) for v in self.step_store.values()):
+            if self._spill_stream is None:
+                self._spill_stream = torch.cuda.Stream()
+            self.attention_store_all_step.append(HostStep(self.step_store, self._spill_stream))
         else:
             self.attention_store_all_step.append(self.step_store)
         self.step_store = self.get_empty_store()
@@ -191,6 +255,8 @@ class AttentionStore(AttentionControl):
                     for d in self.attention_store_all_step:
                         if isinstance(d, str):
                             d = torch.load(d)
+                        elif isinstance(d, HostStep):
+                            d = d.fetch()
                         cur = d.get(k, [])
                         per_pos = [t.clone() for t in cur] if per_pos is None else [a + b for a, b in zip(per_pos, cur)]
                     sums[k] = per_pos or []
@@ -210,7 +276,7 @@ class AttentionStore(AttentionControl):
               "attention_store_paths", "_pos")
 
     def graph_signature(self):
-        if type(self) is not AttentionStore or self.disk_store:
+        if type(self) is not AttentionStore or self.disk_store or self.host_spill:
             return None
         return ("store", bool(self.save_self_attention), bool(self.LOW_RESOURCE))
 
@@ -312,7 +378,7 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
 
     def graph_signature(self):
         """Everything that shapes the launch sequence of the edit loop (table CONTENT is refreshed per replay, see load_tables_from)."""
-        if self.disk_store or self.additional_attention_store is None:
+        if self.disk_store or self.additional_attention_store is None or getattr(self.additional_attention_store, "host_spill", False):
             return None
 
         def blender(b):
@@ -346,9 +412,20 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
         return self.cur_step
 
     def _source_maps(self, step_in_store: int) -> Dict[str, List[torch.Tensor]]:
-        d = self.additional_attention_store.attention_store_all_step[step_in_store]
+        steps = self.additional_attention_store.attention_store_all_step
+        d = steps[step_in_store]
         if isinstance(d, str):
             d = torch.load(d)
+        elif isinstance(d, HostStep):
+            # host-spilled inversion maps: this step was prefetched while the previous one was in use; start the next transfer now and
+            # drop the steps that are behind us (at most two steps' maps are resident)
+            nxt = step_in_store - 1 if self.use_inversion_attention else step_in_store + 1
+            if 0 <= nxt < len(steps) and isinstance(steps[nxt], HostStep):
+                steps[nxt].prefetch()
+            for j, other in enumerate(steps):
+                if isinstance(other, HostStep) and j not in (step_in_store, nxt) and other.dev is not None:
+                    other.release()
+            d = d.fetch()
         return d
 
     # ---- fused protocol -------------------------------------------------------------------------------------------------

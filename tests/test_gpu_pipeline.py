@@ -200,3 +200,22 @@ def test_device_heatmaps_match_host_path(report):
     assert d <= 1.0  # fp16 running sums summed in a different order: at most one grey level
     strips = visualization.show_cross_attention(tok, case["source"], store, 16, ["up", "down"])
     assert len(strips) == case["frames"] and strips[0].shape[1] == 256 * n
+
+
+@pytest.mark.parametrize("name", ["mini_refine", "mini_replace_blend"])
+def test_host_spill_equals_resident(name, monkeypatch, report):
+    """host_spill (maps parked in pinned host memory after every inversion step, prefetched back one step ahead in the edit pass — the mode
+    for clips whose cache exceeds HBM) must give exactly the resident run's latents, and must not keep the inversion maps in HBM."""
+    from fatezero_b200 import controllers
+    case = CASES[name]
+    ref = run_product_case(case)
+    monkeypatch.setenv("FZ_HOST_SPILL", "1")
+    pipe = build_product(case["unet"], case["model_config"])
+    got = run_product_case(case, pipe=pipe)
+    store = pipe.store_controller
+    assert store.host_spill and all(isinstance(s, controllers.HostStep) for s in store.attention_store_all_step)
+    resident = sum(1 for s in store.attention_store_all_step if s.dev is not None)
+    report[f"host_spill_{name}"] = dict(steps=len(store.attention_store_all_step), resident_after_edit=resident)
+    assert resident <= 2
+    assert not pipe._plans  # spilled stores always take the eager loops
+    assert torch.equal(got["inv_latents"], ref["inv_latents"]) and torch.equal(got["edit_latents"], ref["edit_latents"])
