@@ -34,7 +34,7 @@ class AttnArgs(C.Structure):
         ("d", c_int), ("heads", c_int), ("F", c_int), ("BF", c_int),
         ("scale", c_float), ("src_index", C.POINTER(c_int)), ("edit_bf_start", c_int), ("row_mode", c_int),
         ("store", c_void_p), ("base", c_void_p), ("cache_ld", c_ll), ("acc", c_void_p), ("acc_ld", c_ll),
-        ("xedit", c_void_p), ("mask", c_void_p), ("dbg", c_void_p),
+        ("xedit", c_void_p), ("mask", c_void_p), ("dbg", c_void_p), ("causal", c_int),
     ]
 
 
@@ -82,6 +82,8 @@ SIGNATURES = {
     "fz_p2p_push": [C.POINTER(P2PSeg), c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, C.c_uint, c_void_p],
     "fz_p2p_wait": [c_void_p, C.c_uint, c_void_p],
     "fz_gn_combine": [c_void_p, C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "fz_embed_tokens_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "fz_quick_gelu_f16": [c_void_p, c_ll, c_void_p],
     "fz_cross_heatmaps": [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "fz_device_check": [],
     "fz_init": [c_void_p],

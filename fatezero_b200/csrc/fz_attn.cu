@@ -58,6 +58,7 @@ struct AttnParams {
   __half* out;          // [BF*S_q, ldo], this head's columns start at head*d
   long long ldo;
   long long* dbg;       // optional [32] cycle counters written by CTA (0,0,0) (profiling aid)
+  int causal;           // key n visible to query s only if n <= s (kMasked instantiation only)
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -429,6 +430,12 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
             for (int e = 0; e < 64; ++e)
               if (e >= valid) r[e] = 0xff800000u;  // -inf
           }
+          if (p.causal) {
+            const int k0c = atom_info(p, atoms_per_slot, A).k0;
+#pragma unroll
+            for (int e = 0; e < 64; ++e)
+              if (k0c + e > q) r[e] = 0xff800000u;
+          }
         }
         float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
@@ -494,6 +501,11 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
 #pragma unroll
             for (int e = 0; e < 64; ++e)
               if (e >= ai.valid) r[e] = 0xff800000u;
+          }
+          if (p.causal) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e)
+              if (ai.k0 + e > q) r[e] = 0xff800000u;
           }
         }
         float* pv = reinterpret_cast<float*>(r);
@@ -1255,6 +1267,8 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
   p.xedit = a->xedit; p.mask = a->mask;
   p.out = static_cast<__half*>(a->out); p.ldo = a->ldo;
   p.dbg = static_cast<long long*>(a->dbg);
+  p.causal = a->causal;
+  if (a->causal) FZ_CHECK_ARG(a->n_slots == 1 && a->row_mode == FZ_ATTN_NONE && !a->acc, "fz_attention: causal masking needs one slot and no controller hook");
   const int Fc = a->BF - a->edit_bf_start;
   if (a->row_mode == FZ_ATTN_STORE) FZ_CHECK_ARG(a->store, "fz_attention: STORE needs a cache slab");
   if (a->row_mode == FZ_ATTN_REPLACE || a->row_mode == FZ_ATTN_BLEND || a->row_mode == FZ_ATTN_CROSSEDIT)
@@ -1281,7 +1295,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     if (int rc = encode_tmap_f16(&p.tmVt, a->vt, 4, dims, strides, box, true)) return rc;
   }
   // rows without any controller hook and a small head dim take the TMEM-resident-P kernel
-  const bool plain = (a->row_mode == FZ_ATTN_NONE || a->edit_bf_start >= a->BF) && !a->acc && a->d <= 64 &&
+  const bool plain = !a->causal && (a->row_mode == FZ_ATTN_NONE || a->edit_bf_start >= a->BF) && !a->acc && a->d <= 64 &&
                      (a->keys_per_slot % 128 == 0 || a->n_slots == 1) && a->S_q % 128 == 0;
   if (plain) {
     uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->keys_per_slot, (uint64_t)a->n_src};
@@ -1342,7 +1356,7 @@ extern "C" int fz_attention_f16(const fz_attn_args_t* a, cudaStream_t stream) {
     configured = smem;
   }
   dim3 grid((a->S_q + 127) / 128, a->heads, a->BF);
-  if (a->keys_per_slot % 64 == 0) FZ_CUDA(launch_pdl(attn_kernel<false>, grid, dim3(320), smem, stream, p));
+  if (a->keys_per_slot % 64 == 0 && !a->causal) FZ_CUDA(launch_pdl(attn_kernel<false>, grid, dim3(320), smem, stream, p));
   else FZ_CUDA(launch_pdl(attn_kernel<true>, grid, dim3(320), smem, stream, p));
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;

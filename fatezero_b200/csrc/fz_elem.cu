@@ -1021,3 +1021,36 @@ extern "C" int fz_cross_heatmaps(const void* const* maps, int num_maps, int maps
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CLIP text encoder helpers (the transformer itself runs on fz_layernorm / fz_gemm / fz_attention with causal = 1)
+// ---------------------------------------------------------------------------------------------------------------
+namespace fz {
+__global__ void embed_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ pos, const long long* __restrict__ ids,
+                                    __half* __restrict__ out, int rows, int L, int C) {
+  const int r = blockIdx.x;
+  const long long id = ids[r];
+  const float* t = tok + id * C;
+  const float* pp = pos + static_cast<long long>(r % L) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[static_cast<long long>(r) * C + c] = __float2half_rn(t[c] + pp[c]);
+}
+__global__ void quick_gelu_kernel(__half* __restrict__ x, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __half2float(x[i]);
+    x[i] = __float2half_rn(v / (1.0f + __expf(-1.702f * v)));
+  }
+}
+}  // namespace fz
+
+extern "C" int fz_embed_tokens_f16(const float* tok, const float* pos, const long long* ids, void* out, int rows, int L, int C, cudaStream_t stream) {
+  FZ_CHECK_ARG(tok && pos && ids && out && rows > 0 && L > 0 && C > 0, "fz_embed_tokens: bad args");
+  fz::embed_tokens_kernel<<<rows, 256, 0, stream>>>(tok, pos, ids, static_cast<__half*>(out), rows, L, C);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}
+extern "C" int fz_quick_gelu_f16(void* x, long long n, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && n > 0, "fz_quick_gelu: bad args");
+  fz::quick_gelu_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(static_cast<__half*>(x), n);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}

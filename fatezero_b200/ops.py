@@ -260,6 +260,21 @@ def blend_mask(maps: Sequence[torch.Tensor], word_w: torch.Tensor, th: float, h:
     return out
 
 
+def embed_tokens(tok: torch.Tensor, pos: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """tok [V, C] fp32, pos [L, C] fp32, ids [B, L] int64 (CUDA) -> [B*L, C] fp16."""
+    B, L = ids.shape
+    out = torch.empty((B * L, tok.shape[1]), dtype=f16, device=tok.device)
+    _lib.call("fz_embed_tokens_f16", _p(tok), _p(pos), _p(ids.contiguous()), _p(out), B * L, L, tok.shape[1], _stream())
+    return out
+
+
+def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, f16, "quick_gelu")
+    assert x.is_contiguous()
+    _lib.call("fz_quick_gelu_f16", _p(x), x.numel(), _stream())
+    return x
+
+
 def cross_heatmaps(maps: Sequence[torch.Tensor], ntok: int) -> torch.Tensor:
     """maps: cross-attention running sums [F, heads, r*r, ld] (fp16 or fp32) of ONE resolution -> uint8 [F, ntok, r, r] heat maps."""
     m0 = maps[0]
@@ -273,7 +288,8 @@ def cross_heatmaps(maps: Sequence[torch.Tensor], ntok: int) -> torch.Tensor:
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, S_q: int, keys_per_slot: int, n_src: int, d: int,
               heads: int, F: int, BF: int, scale: float, src_index: Sequence[Sequence[int]], edit_bf_start: int = 0,
-              row_mode: int = _lib.ATTN_NONE, store=None, base=None, cache_ld: int = 0, acc=None, xedit=None, mask=None, dbg=None):
+              row_mode: int = _lib.ATTN_NONE, store=None, base=None, cache_ld: int = 0, acc=None, xedit=None, mask=None, dbg=None,
+              causal: bool = False):
     """q/k: strided 2-D views (rows, ld) whose column h*d starts head h; vt [n_src, heads, d, vt_ld]; out [BF*S_q, ldo]."""
     a = AttnArgs()
     a.q, a.ldq = _p(q), q.stride(0)
@@ -291,5 +307,6 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     a.acc, a.acc_ld = _p(acc), (acc.stride(2) if acc is not None else 0)
     a.xedit, a.mask = _p(xedit), _p(mask)
     a.dbg = _p(dbg)
+    a.causal = int(causal)
     _lib.call("fz_attention_f16", C.byref(a), _stream())
     return out

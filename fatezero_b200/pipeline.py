@@ -139,6 +139,24 @@ class SpatioTemporalStableDiffusionPipeline:
         if params_to_optimize is not None:
             params_to_optimize.requires_grad = True
 
+    def _text_forward(self, ids, mask):
+        """The text encoder call of stable_diffusion.py:230,279.  A transformers CLIPTextModel living on the GPU is executed by
+        clip.ClipTextEngine (sm_100a kernels, built once per module); any other module — or a padding mask — is simply called."""
+        te = self.text_encoder
+        if (mask is None and os.environ.get("FZ_CLIP", "1") != "0" and type(te).__name__ == "CLIPTextModel" and isinstance(te, torch.nn.Module)
+                and next(te.parameters()).is_cuda):
+            eng = getattr(self, "_clip_engine", None)
+            if eng is None or eng[0] is not te:
+                from .clip import ClipTextEngine
+                try:
+                    eng = (te, ClipTextEngine(te))
+                except NotImplementedError:
+                    eng = (te, None)
+                self._clip_engine = eng
+            if eng[1] is not None:
+                return eng[1](ids)[0]
+        return te(ids, attention_mask=mask)[0]
+
     def _encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt):
         """stable_diffusion.py:180-295: [uncond ; cond] text embeddings of shape [2*b, 77, D]."""
         batch_size = len(prompt) if isinstance(prompt, list) else 1
@@ -147,7 +165,7 @@ class SpatioTemporalStableDiffusionPipeline:
         ids = text_inputs.input_ids
         use_mask = bool(getattr(getattr(self.text_encoder, "config", None), "use_attention_mask", False))
         mask = text_inputs.attention_mask.to(device) if use_mask else None
-        emb = self.text_encoder(ids.to(device), attention_mask=mask)[0]
+        emb = self._text_forward(ids.to(device), mask)
         bs, seq, _ = emb.shape
         emb = emb.repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
         if do_classifier_free_guidance:
@@ -164,7 +182,7 @@ class SpatioTemporalStableDiffusionPipeline:
                 uncond_tokens = negative_prompt
             un = tok(uncond_tokens, padding="max_length", max_length=ids.shape[-1], truncation=True, return_tensors="pt")
             umask = un.attention_mask.to(device) if use_mask else None
-            uemb = self.text_encoder(un.input_ids.to(device), attention_mask=umask)[0]
+            uemb = self._text_forward(un.input_ids.to(device), umask)
             uemb = uemb.repeat(1, num_images_per_prompt, 1).view(batch_size * num_images_per_prompt, uemb.shape[1], -1)
             emb = torch.cat([uemb, emb])
         return emb

@@ -103,6 +103,7 @@ typedef struct fz_attn_args {
   const float* xedit;               /* device table, see above                                                       */
   const float* mask;                /* device [BF-edit_bf_start, S_q], 1 = keep current row                          */
   void* dbg;                        /* optional device int64[32]: cycle counters of CTA (0,0,0) (profiling aid) or NULL */
+  int causal;                       /* 1: key n is visible to query s only if n <= s (CLIP text encoder; needs n_slots == 1, row_mode NONE) */
 } fz_attn_args_t;
 
 int fz_attention_f16(const fz_attn_args_t* args, fz_stream_t stream);
@@ -147,6 +148,11 @@ int fz_cfg_ddim_step(float* x, const float* eps2, long long n, float guidance, f
 /* blend mask from cached cross maps (spatial_blend.py:24-39,78-111); maps: HOST array of device pointers, word_w: HOST [ntok] */
 int fz_blend_mask(const void* const* maps, int num_maps, int maps_f32, int F, int heads, int r, int ldm, int ntok, const float* word_w,
                   float th, int h, int w, float* out, fz_stream_t stream);
+
+/* CLIP text encoder pieces (pipelines/stable_diffusion.py:230,279 call transformers' CLIPTextModel): token + position embedding rows
+ * out[r, :] = fp16(tok[ids[r], :] + pos[r % L, :]) and the quick_gelu activation x * sigmoid(1.702 x) in place. */
+int fz_embed_tokens_f16(const float* tok, const float* pos, const long long* ids, void* out, int rows, int L, int C, fz_stream_t stream);
+int fz_quick_gelu_f16(void* x, long long n, fz_stream_t stream);
 
 /* show_cross_attention on the device (prompt_attention/visualization.py:14-72): out[f, tok, res*res] = 255 * a / max(a) with a = sum over the
  * given cross-attention maps ([F, heads, res*res, ldm] fp16 or fp32 running sums) and heads of the probability of text token tok (the means'
