@@ -27,7 +27,7 @@ def test_clip_engine_matches_transformers(report):
     d = (got - ref).abs().max().item()
     report["clip_text"] = dict(max_abs=d, ref_abs_max=ref.abs().max().item(), rms=(got - ref).pow(2).mean().sqrt().item())
     print(f"\nCLIP text encoder: max|d| {d:.3e} on max|h| {ref.abs().max().item():.2f}")
-    assert d < 2e-2 * max(1.0, ref.abs().max().item())
+    assert d < 1.7e-2  # measured 8.5e-3 on max|h| 4.55 (fp16 residual stream through 12 layers)
     # causality: changing a later token must not change earlier positions
     ids2 = ids.clone()
     ids2[1, 40] = 1234
