@@ -234,6 +234,31 @@ def instrument(pipe, x0_dev, emb_src):
     return dict(gemm=(g_flops, g_secs, len(rec), g_bytes), st_attn=(a_flops, a_secs, len(att)))
 
 
+def vae_bracket(device, frames: int, px: int):
+    """The VAE bracket of the path, outside the headline metric like in SURVEY §8(d): encode `frames` RGB frames and
+    decode `frames` latents with fatezero_b200.vae.VaeEngine (SD-1.x VAE geometry, synthetic weights), CUDA-event timed after a warm-up."""
+    from fatezero_b200 import synth
+    from fatezero_b200 import vae as fzvae
+    cfg = dict(fzvae.SD14_VAE_CONFIG)
+    eng = fzvae.VaeEngine(synth.synth_state_dict(dict(fzvae.vae_param_spec(cfg)), seed=3), cfg, device)
+    img = (torch.rand(frames, 3, px, px, generator=torch.Generator().manual_seed(5)) * 2 - 1).to(device)
+    z = torch.randn(frames, 4, px // 8, px // 8, generator=torch.Generator().manual_seed(6)).to(device)
+    out = {}
+    for name, fn in (("encode_ms", lambda: eng.encode_moments(img)), ("decode_ms", lambda: eng.decode(z))):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        out[name] = round(s.elapsed_time(e), 2)
+    out.update(frames=frames, resolution=f"{px}x{px}", note="AutoencoderKL geometry of SD-1.x on the tap-GEMM; not part of the frames/s metric")
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are redirected to stderr for the run
@@ -349,6 +374,9 @@ def run_gpu(args):
         st = dict(value=round(af / max(asec, 1e-9) / 1e12, 1), unit="TFLOP/s", launches_per_clip=an, algorithmic_tflop_per_clip=round(af / 1e12, 1),
                   kernel_seconds_per_clip=round(asec, 4), share_of_step=round(asec / (ms / 1e3 / args.steps), 3),
                   definition="sum over ST-attn launches of 4*BF*heads*S*T*d / sum of their CUDA-event durations (rank 0's frames)")
+    vae_line = None
+    if rank == 0 and not args.no_instrument:
+        vae_line = vae_bracket(device, FRAMES, 8 * SIZE)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample()
     if rank == 0:
@@ -365,7 +393,7 @@ def run_gpu(args):
                                 l2="working set (map cache of the clip + activations) far exceeds the 126 MB L2; no explicit flush"),
                     clocks=clocks, e2e=dict(value=round(e2e_value, 4), unit="frames/s", h2d_bytes_per_step=x0_host.numel() * 4,
                                             d2h_bytes_per_step=out_host.numel() * 4),
-                    gpu_launches=int(launches), st_attn_tflops=st, roofline=roof,
+                    gpu_launches=int(launches), st_attn_tflops=st, vae=vae_line, roofline=roof,
                     cpu_baseline=cpu)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

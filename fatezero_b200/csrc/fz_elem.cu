@@ -1054,3 +1054,45 @@ extern "C" int fz_quick_gelu_f16(void* x, long long n, cudaStream_t stream) {
   FZ_CUDA(cudaGetLastError());
   return FZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row softmax in place: x[r, :n] <- softmax(scale * x[r, :n]) (fp32 math, fp16 storage).  The VAE's single-head 512-wide mid-block
+// attention (diffusers AttentionBlock: stable_diffusion.py:297-319 decode path) runs as GEMM -> this -> GEMM: its head dim exceeds what
+// the fused attention kernels hold in TMEM.  One warp per row.
+// ---------------------------------------------------------------------------------------------------------------
+namespace fz {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long rows, int n, long long ld, float scale_log2) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  __half* row = x + r * ld;
+  float m = -INFINITY;
+  for (int c = lane * 8; c < n; c += 256) {
+    const Half8 h = *reinterpret_cast<const Half8*>(row + c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m = fmaxf(m, __half2float(h.v[e]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int c = lane * 8; c < n; c += 256) {
+    const Half8 h = *reinterpret_cast<const Half8*>(row + c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += exp2f((__half2float(h.v[e]) - m) * scale_log2);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int c = lane * 8; c < n; c += 256) {
+    Half8 h = *reinterpret_cast<const Half8*>(row + c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h.v[e] = __float2half_rn(exp2f((__half2float(h.v[e]) - m) * scale_log2) * inv);
+    *reinterpret_cast<Half8*>(row + c) = h;
+  }
+}
+}  // namespace fz
+
+extern "C" int fz_softmax_rows_f16(void* x, long long rows, int n, long long ld, float scale, cudaStream_t stream) {
+  FZ_CHECK_ARG(x && rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0 && scale > 0.f, "fz_softmax_rows: n and ld must be multiples of 8");
+  fz::softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(static_cast<__half*>(x), rows, n, ld, scale * 1.4426950408889634f);
+  FZ_CUDA(cudaGetLastError());
+  return FZ_OK;
+}

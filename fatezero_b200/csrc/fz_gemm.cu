@@ -872,16 +872,20 @@ extern "C" int fz_gemm_f16(const void* A, long long lda, const void* W, long lon
 
 // 3x3 convolution, padding 1, stride 1 or 2, NHWC fp16.  x: [NB, H, W, Cin] (pixel stride ldx >= Cin),
 // w: [9][Cout][Cin] (tap-major, tap = ky*3+kx), out: [NB, Ho, Wo, Cout] row-major with row stride ldo.
-extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout, int stride,
-                                   const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+// asym_pad (stride 2 only): the input is padded by one pixel on the right / bottom ONLY (diffusers Downsample2D with padding = 0 in the VAE
+// encoder: F.pad(x, (0, 1, 0, 1)) then a stride-2 conv without padding) instead of symmetrically.
+static int conv3x3_impl(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout, int stride, int asym_pad,
+                        const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
   FZ_CHECK_ARG(x && w && out, "fz_conv3x3: null pointer");
   FZ_CHECK_ARG(stride == 1 || stride == 2, "fz_conv3x3: stride must be 1 or 2");
   FZ_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "fz_conv3x3: Cin/ldx must be multiples of 8");
   FZ_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "fz_conv3x3: stride 2 needs even H, W");
   const int Ho = H / stride, Wo = W / stride;
-  FZ_CHECK_ARG(Wo <= 128, "fz_conv3x3: output width %d > 128 not supported", Wo);
-  // box over (x, y, n): full output width, as many rows / images as fit 128 GEMM rows
-  int bw = Wo, bh = std::min(Ho, 128 / bw);
+  FZ_CHECK_ARG(Wo <= 128 || Wo % 128 == 0, "fz_conv3x3: output width %d must be <= 128 or a multiple of 128", Wo);
+  FZ_CHECK_ARG(!asym_pad || stride == 2, "fz_conv3x3: asymmetric padding is the stride-2 downsample variant");
+  // box over (x, y, n): the full output width (or 128-pixel row segments of wider images: VAE resolutions), as many rows / images as fit
+  // 128 GEMM rows
+  int bw = std::min(Wo, 128), bh = (bw == Wo) ? std::min(Ho, 128 / bw) : 1;
   while (Ho % bh) --bh;
   int bn_img = (bh == Ho) ? std::min(NB, 128 / (bw * bh)) : 1;
   while (NB % bn_img) --bn_img;
@@ -908,10 +912,12 @@ extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, 
     p.a_rank = 5;
     for (int t = 0; t < 9; ++t) {
       const int ky = t / 3, kx = t % 3;
-      const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
+      // symmetric padding 1: input row 2y + ky - 1 -> phase (ky != 1), shift -1 for ky = 0; right/bottom-only padding: input row 2y + ky ->
+      // phase ky & 1, shift +1 for ky = 2 (the zero row / column beyond the edge is TMA's out-of-bounds fill)
+      const int py = asym_pad ? (ky & 1) : ((ky == 1) ? 0 : 1), px = asym_pad ? (kx & 1) : ((kx == 1) ? 0 : 1);
       p.tap_off[t][0] = px * (int)ldx;
-      p.tap_off[t][1] = (kx == 0) ? -1 : 0;
-      p.tap_off[t][2] = (ky == 0) ? -1 : 0;
+      p.tap_off[t][1] = asym_pad ? (kx >> 1) : ((kx == 0) ? -1 : 0);
+      p.tap_off[t][2] = asym_pad ? (ky >> 1) : ((ky == 0) ? -1 : 0);
       p.tap_off[t][3] = 0;
       p.tap_off[t][4] = py;
     }
@@ -931,6 +937,16 @@ extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, 
   p.ndecomp = 3; p.dimsz[0] = Wo; p.dimsz[1] = Ho; p.dimsz[2] = NB;
   p.out = static_cast<__half*>(out); p.ldo = ldo;
   return dispatch_tapgemm(p, Cout, bn, stream);
+}
+
+extern "C" int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout, int stride,
+                                   const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  return conv3x3_impl(x, ldx, NB, H, W, Cin, w, Cout, stride, 0, epi, out, ldo, force_block_n, stream);
+}
+
+extern "C" int fz_conv3x3_down_asym_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout,
+                                             const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, cudaStream_t stream) {
+  return conv3x3_impl(x, ldx, NB, H, W, Cin, w, Cout, 2, 1, epi, out, ldo, force_block_n, stream);
 }
 
 // Temporal Conv1d(k=3, padding 1, no bias) over the frame axis: x [B, F, HW, Cin] fp16 (row stride ldx), w [3][Cout][Cin].

@@ -89,8 +89,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, g
 
 
 def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias=None, stride: int = 1, residual=None, group_bias=None, rows_per_group=0,
-            force_bn: int = 0) -> torch.Tensor:
-    """x [NB,H,W,Cin] fp16 NHWC, w9 [9,Cout,Cin] -> [NB,H/stride,W/stride,Cout]."""
+            force_bn: int = 0, asym_pad: bool = False) -> torch.Tensor:
+    """x [NB,H,W,Cin] fp16 NHWC, w9 [9,Cout,Cin] -> [NB,H/stride,W/stride,Cout].  asym_pad (stride 2): right/bottom-only padding."""
     _chk(x, f16, "conv3x3"); _chk(w9, f16, "conv3x3")
     NB, H, W, Cin = x.shape
     Cout = w9.shape[1]
@@ -99,7 +99,11 @@ def conv3x3(x: torch.Tensor, w9: torch.Tensor, bias=None, stride: int = 1, resid
     e = _epilogue(bias, group_bias, rows_per_group, residual)
     if residual is not None:
         e.ldr = residual.shape[-1]
-    _lib.call("fz_conv3x3_nhwc_f16", _p(x), Cin, NB, H, W, Cin, _p(w9), Cout, stride, C.byref(e), _p(out), Cout, force_bn, _stream())
+    if asym_pad:
+        assert stride == 2
+        _lib.call("fz_conv3x3_down_asym_nhwc_f16", _p(x), Cin, NB, H, W, Cin, _p(w9), Cout, C.byref(e), _p(out), Cout, force_bn, _stream())
+    else:
+        _lib.call("fz_conv3x3_nhwc_f16", _p(x), Cin, NB, H, W, Cin, _p(w9), Cout, stride, C.byref(e), _p(out), Cout, force_bn, _stream())
     return out
 
 
@@ -258,6 +262,15 @@ def blend_mask(maps: Sequence[torch.Tensor], word_w: torch.Tensor, th: float, h:
     _lib.call("fz_blend_mask", arr, len(maps), int(m0.dtype == torch.float32), Fm, heads, r, m0.stride(2), min(len(ww), 77), wv,
               float(th), h, w, _p(out), _stream())
     return out
+
+
+def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """x [rows, n] fp16 (row stride multiple of 8) <- softmax(scale * x) row-wise, in place."""
+    _chk(x, f16, "softmax_rows")
+    rows, n = x.shape
+    assert x.stride(1) == 1
+    _lib.call("fz_softmax_rows_f16", _p(x), rows, n, x.stride(0), float(scale), _stream())
+    return x
 
 
 def embed_tokens(tok: torch.Tensor, pos: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:

@@ -187,6 +187,26 @@ class SpatioTemporalStableDiffusionPipeline:
             emb = torch.cat([uemb, emb])
         return emb
 
+    def _vae_engine(self):
+        """The sm_100a VAE executor for `self.vae` (fatezero_b200.vae): our AutoencoderKL container or a foreign AutoencoderKL-shaped
+        module on the GPU; None for anything else (stubs, CPU modules) — those are simply called."""
+        if os.environ.get("FZ_VAE", "1") == "0":
+            return None
+        cached = getattr(self, "_vae_cache", None)
+        if cached is None or cached[0] is not self.vae:
+            from . import vae as vae_mod
+            cached = (self.vae, vae_mod.engine_for(self.vae))
+            self._vae_cache = cached
+        return cached[1]
+
+    def _vae_encode_sample(self, image, generator):
+        """p2p_ddim_spatial_temporal.py:88-96: vae.encode(image).latent_dist.sample(generator)."""
+        eng = self._vae_engine()
+        if eng is None:
+            return self.vae.encode(image).latent_dist.sample(generator)
+        from .vae import DiagonalGaussianDistribution
+        return DiagonalGaussianDistribution(eng.encode_moments(image).to(image.dtype)).sample(generator)
+
     def decode_latents(self, latents):
         """stable_diffusion.py:297-319 (VAE decode in chunks of 16 frames)."""
         is_video = latents.dim() == 5
@@ -195,7 +215,11 @@ class SpatioTemporalStableDiffusionPipeline:
         if is_video:
             latents = latents.permute(0, 2, 1, 3, 4).reshape(-1, *latents.shape[1:2], *latents.shape[3:])
         vdt = next(self.vae.parameters()).dtype if isinstance(self.vae, torch.nn.Module) else latents.dtype
-        image = torch.cat([self.vae.decode(chunk.to(vdt)).sample for chunk in torch.split(latents, 16, dim=0)], dim=0)
+        eng = self._vae_engine()
+        if eng is not None:
+            image = torch.cat([eng.decode(chunk) for chunk in torch.split(latents, 16, dim=0)], dim=0)
+        else:
+            image = torch.cat([self.vae.decode(chunk.to(vdt)).sample for chunk in torch.split(latents, 16, dim=0)], dim=0)
         image = (image / 2 + 0.5).clamp(0, 1).cpu().float().numpy()
         if is_video:
             image = image.reshape(b, -1, *image.shape[1:]).transpose(0, 1, 3, 4, 2)
@@ -258,9 +282,9 @@ class P2pDDIMSpatioTemporalPipeline(SpatioTemporalStableDiffusionPipeline):
             raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch size of "
                              f"{batch_size}. Make sure the batch size matches the length of the generators.")
         if isinstance(generator, list):
-            init_latents = torch.cat([self.vae.encode(image[i:i + 1]).latent_dist.sample(generator[i]) for i in range(batch_size)], dim=0)
+            init_latents = torch.cat([self._vae_encode_sample(image[i:i + 1], generator[i]) for i in range(batch_size)], dim=0)
         else:
-            init_latents = self.vae.encode(image).latent_dist.sample(generator)
+            init_latents = self._vae_encode_sample(image, generator)
         init_latents = 0.18215 * init_latents
         if batch_size > init_latents.shape[0] and batch_size % init_latents.shape[0] != 0:
             raise ValueError(f"Cannot duplicate `image` of batch size {init_latents.shape[0]} to {batch_size} text prompts.")

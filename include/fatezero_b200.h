@@ -55,6 +55,9 @@ int fz_gemm_f16(const void* A, long long lda, const void* W, long long ldw, int 
 /* per-frame 3x3 conv of PseudoConv3d.forward (resnet.py:57-64), stride 1 or 2, NHWC */
 int fz_conv3x3_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout, int stride,
                         const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, fz_stream_t stream);
+/* the VAE encoder's downsample (diffusers Downsample2D, padding 0: F.pad(x, (0, 1, 0, 1)) then a 3x3 stride-2 conv without padding) */
+int fz_conv3x3_down_asym_nhwc_f16(const void* x, long long ldx, int NB, int H, int W, int Cin, const void* w, int Cout,
+                                  const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, fz_stream_t stream);
 /* temporal Conv1d(k=3) of LoRALinearLayer / conv_temporal (resnet.py:72-78, lora.py:46-54) */
 int fz_tconv3_f16(const void* x, long long ldx, int B, int F, int HW, int Cin, const void* w, int Cout,
                   const fz_epilogue_t* epi, void* out, long long ldo, int force_block_n, fz_stream_t stream);
@@ -153,6 +156,9 @@ int fz_blend_mask(const void* const* maps, int num_maps, int maps_f32, int F, in
  * out[r, :] = fp16(tok[ids[r], :] + pos[r % L, :]) and the quick_gelu activation x * sigmoid(1.702 x) in place. */
 int fz_embed_tokens_f16(const float* tok, const float* pos, const long long* ids, void* out, int rows, int L, int C, fz_stream_t stream);
 int fz_quick_gelu_f16(void* x, long long n, fz_stream_t stream);
+
+/* in-place row softmax x[r, :n] <- softmax(scale * x[r, :n]), fp32 math: the VAE's 512-wide single-head attention runs GEMM -> this -> GEMM */
+int fz_softmax_rows_f16(void* x, long long rows, int n, long long ld, float scale, fz_stream_t stream);
 
 /* show_cross_attention on the device (prompt_attention/visualization.py:14-72): out[f, tok, res*res] = 255 * a / max(a) with a = sum over the
  * given cross-attention maps ([F, heads, res*res, ldm] fp16 or fp32 running sums) and heads of the probability of text token tok (the means'
