@@ -62,6 +62,9 @@ CFG = dict(CONFIGS["style"], name="style")
 def select_config(name: str):
     CFG.clear()
     CFG.update(CONFIGS[name], name=name)
+    if os.environ.get("FZ_BENCH_FRAMES"):  # development: e.g. 1 frame on one GPU = what one rank of an 8-GPU frame-sharded run computes
+        CFG["frames"] = int(os.environ["FZ_BENCH_FRAMES"])
+        CFG["workload"] += f" [frames overridden: {CFG['frames']}]"
 
 
 def peaks():

@@ -103,14 +103,12 @@ class UNetEngine:
         rank, world, _ = self.shard
         ar = self.arena
         NB, G = x3.shape[0], self.groups
-        nb = NB * G * 8
+        nb = NB * G * 16                                                   # two 8-byte {value, epoch} words per (image, group)
         sums = ops.groupnorm_stats(x3, G)                                  # [NB, G, 2] fp32 view into the workspace
         site = ar.site(("gn", name, NB), world * nb)
-        st = ops._stream()
-        pf = (C.c_void_p * world)(*[ar.flag_ptr(r, site, rank) if r != rank else None for r in range(world)])
         pi = (C.c_void_p * world)(*[ar.peer_ptr(r, site, rank * nb) if r != rank else None for r in range(world)])
-        _lib.call("fz_gn_combine", C.c_void_p(ar.base + site.flag_offset), pf, pi, C.c_void_p(ar.base + site.offset), C.c_void_p(sums.data_ptr()),
-                  NB, F, G, world, rank, st)
+        _lib.call("fz_gn_combine", C.c_void_p(ar.base + site.flag_offset + 4 * 31), pi, C.c_void_p(ar.base + site.offset),
+                  C.c_void_p(sums.data_ptr()), NB, F, G, world, rank, ops._stream())
         return ops.groupnorm_apply(x3, gamma, beta, eps, G, F, F * world, silu, sums)
 
     def _halo_ext(self, key: tuple, y4: torch.Tensor) -> torch.Tensor:

@@ -197,11 +197,12 @@ int fz_p2p_push(const fz_p2p_seg_t* segs, int n_segs, void* const* flags, void* 
                 fz_stream_t stream);
 /* flags: local array of up to 32 flag words; waits for (and clears) those selected by mask */
 int fz_p2p_wait(void* flags, unsigned mask, fz_stream_t stream);
-/* GroupNorm statistics exchange in one launch: pushes sums [NB*G] float2 into peer_inbox[r] (rank r's inbox slot for this rank), raises
- * peer_flags[r], waits for the peers' flags (local `flags`, one word per source), then adds the peers' statistics (inbox [world][NB*G]
- * float2, local) to sums, leaving each statistics set's total in the slot of its first local image (input layout of fz_groupnorm_apply_f16) */
-int fz_gn_combine(void* flags, void* const* peer_flags, void* const* peer_inbox, const void* inbox, void* sums, int NB, int F_loc, int G,
-                  int world, int me, fz_stream_t stream);
+/* GroupNorm statistics exchange in one single-CTA launch, low-latency protocol: every (sum, sumsq) of sums [NB*G] float2 is written into
+ * peer_inbox[r] (rank r's inbox slot for this rank, [NB*G][2] 8-byte words {value, epoch}); the kernel then polls the local inbox
+ * ([world][NB*G][2] words) until every peer's words carry this use's epoch (`epoch`: local per-site counter, advanced by the kernel), adds
+ * them to sums and leaves each statistics set's total in the slot of its first local image (input layout of fz_groupnorm_apply_f16). */
+int fz_gn_combine(void* epoch, void* const* peer_inbox, const void* inbox, void* sums, int NB, int F_loc, int G, int world, int me,
+                  fz_stream_t stream);
 
 #ifdef __cplusplus
 }

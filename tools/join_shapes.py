@@ -18,7 +18,7 @@ def main():
         if r["Metric Name"] != "gpu__time_duration.sum" or r["ID"] in seen:
             continue
         name = r["Kernel Name"]
-        if "tapgemm" in name or "attn_kernel" in name or "attn_plain" in name or "attn_cross" in name:
+        if "temporal" not in name and ("tapgemm" in name or "attn_kernel" in name or "attn_plain" in name or "attn_cross" in name):
             seen.add(r["ID"])
             v = float(r["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}[r["Metric Unit"]]
             dur.append((re.sub(r"\(.*", "", name).replace("void ", "").replace("fz::", ""), v))
