@@ -199,3 +199,13 @@ def test_frame_shard_exchange_gloo_world_size_2():
         p.join(60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_vae_spec_is_the_published_sd_vae():
+    """The AutoencoderKL layout the VAE engine expects: 248 tensors, 83 653 863 parameters (the SD-1.x VAE) — the one fact about diffusers'
+    model that can be checked without the package (the VAE restatement is otherwise unpinned)."""
+    from fatezero_b200 import vae
+    spec = vae.vae_param_spec(vae.SD14_VAE_CONFIG)
+    assert len(spec) == 248
+    assert sum(int(torch.tensor(v).prod()) for v in spec.values()) == 83_653_863
+    assert spec["encoder.mid_block.attentions.0.query.weight"] == (512, 512) and spec["quant_conv.weight"] == (8, 8, 1, 1)

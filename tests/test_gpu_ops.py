@@ -268,3 +268,36 @@ def test_limits_conv_width_and_groupnorm_batch(report):
     close(y, refg, report, "groupnorm_nb256_g64", atol=2e-2, rtol=2e-3)
     with pytest.raises(RuntimeError, match="workspace|unsupported"):
         ops.groupnorm(rnd(257, 16, 128).half(), g, b, 1e-5, 64, 1, False)
+
+
+def test_small_m_long_k(report):
+    """Small-M problems with long k-loops (the r = 8 layers: a few dozen tiles with 60-180 serial k-blocks each), bitwise reproducible.
+    (A deterministic split-K variant of the tap-GEMM was built and measured in round 2: 698 vs 682 ms per 1-frame clip, 1897 vs 1889 ms per
+    8-frame clip — the dump / fence / atomic / read-back of the partial tiles cost what the shorter k-loops saved, so it was dropped.)"""
+    # 3x3 conv 1280 -> 1280 at 8x8, 8 images (180 k-blocks, 4 M tiles)
+    x = rnd(8, 8, 8, 1280).half()
+    w = rnd(1280, 1280, 3, 3, scale=(1280 * 9) ** -0.5, seed=1)
+    b = rnd(1280, seed=2) * 0.1
+    res = rnd(8, 8, 8, 1280, seed=4).half()
+    w9 = w.permute(2, 3, 0, 1).reshape(9, 1280, 1280).half().contiguous()
+    out = ops.conv3x3(x, w9, bias=b, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w9.float().reshape(3, 3, 1280, 1280).permute(2, 3, 0, 1), b, padding=1).permute(0, 2, 3, 1) + res.float()
+    close(out, ref, report, "small_m_conv_r8", atol=2e-2, rtol=2e-3)
+    assert torch.equal(out, ops.conv3x3(x, w9, bias=b, residual=res))
+    # one image (64 rows: half an M tile)
+    out1 = ops.conv3x3(x[:1].contiguous(), w9, bias=b)
+    close(out1, ref[:1] - res[:1].float(), report, "small_m_conv_r8_one_image", atol=2e-2, rtol=2e-3)
+    # linear 512 x 1280 x 5120 with bias + skip (80 k-blocks)
+    a = rnd(512, 5120, seed=5).half()
+    wl = rnd(1280, 5120, scale=5120 ** -0.5, seed=6).half()
+    r2 = rnd(512, 1280, seed=7).half()
+    got = ops.gemm(a, wl, bias=b, residual=r2)
+    close(got, a.float() @ wl.float().t() + b + r2.float(), report, "small_m_linear", atol=2e-2, rtol=2e-3)
+    assert torch.equal(got, ops.gemm(a, wl, bias=b, residual=r2))
+    # temporal conv 1280 -> 160 over 8 frames of 64 pixels (60 k-blocks)
+    xt = rnd(2, 8, 64, 1280, seed=8).half()
+    w3 = rnd(3, 160, 1280, scale=(3 * 1280) ** -0.5, seed=9).half()
+    yt = ops.tconv3(xt, w3)
+    xp = F.pad(xt.float(), (0, 0, 0, 0, 1, 1))
+    reft = sum(torch.einsum("bfpc,oc->bfpo", xp[:, t:t + 8], w3[t].float()) for t in range(3))
+    close(yt, reft, report, "small_m_tconv", atol=2e-2, rtol=2e-3)
