@@ -464,7 +464,7 @@ def run_reference(args):
     F = int(os.environ.get("FZ_REF_FRAMES", CFG["frames"]))  # tests/test_bench_contract.py shrinks the sample; the driver never sets it
     times = []
     t_start = time.perf_counter()
-    budget = float(os.environ.get("FZ_REF_BUDGET_S", "240"))
+    budget = float(os.environ.get("FZ_REF_BUDGET_S", "150"))
     for i in range(args.warmup + args.steps):
         t_inv, t_edit = cpu_sample_seconds(F)
         if i >= min(args.warmup, 1):  # at most one untimed pass: every pass costs the better part of a minute
