@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
 files="$@"
-[ -z "$files" ] && files=$(ls tests/test_gpu_*.py)
+[ -z "$files" ] && files=$(ls tests/test_gpu_*.py tests/test_boundary_logger.py)
 rc_all=0
 for f in $files; do
   name=$(basename $f .py)
