@@ -8,9 +8,12 @@ e2e     : the same edit through the reference-facing API with HOST buffers: per 
           memory and the edited latents are read back to the host inside the timed region.
 roofline: the dominant kernel is the tcgen05 tap-GEMM (convs + linears + temporal LoRA, 86% of the FLOPs): algorithmic FLOPs of all its
           launches in one clip edit / the sum of their CUDA-event durations (instrumented extra pass), against the measured bf16 peak.
-Launch:  python bench.py [--gpus N --steps K --warmup W]   (N>1 under torch.distributed.run, one rank per GPU: independent clips per
-         rank, "weak" scaling, no data-path collective yet — see DESIGN.md §multi-GPU)
-         python bench.py --impl reference ...               (CPU arm: the oracle port of the reference on the host cores)
+st_attn : ST-attn TFLOPS = sum over the spatio-temporal attention launches of a clip of 4*BF*heads*S*T*d / sum of their CUDA-event durations.
+vae     : the VAE bracket (encode + decode of the clip's frames on the tap-GEMM), reported next to the metric, not inside it.
+Launch:  python bench.py [--gpus N --steps K --warmup W] [--config style|attribute|long24|shape768]
+         N>1 under torch.distributed.run, one rank per GPU: the frames of ONE clip are split over the ranks with the same weights as N=1
+         ("strong" scaling; exchanges = peer-memory push/flag kernels); --shard clips = independent clips per rank (replicas)
+         python bench.py --impl reference ...   (CPU arm: the oracle port of the reference on the host cores, one full-frame step pair per step)
 """
 from __future__ import annotations
 

@@ -1,5 +1,6 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed).  Round 1 shards CLIPS over ranks (independent replicas, no data-path
-collective); the frame-sharded path (K/V exchange + GroupNorm-statistics all-reduce) builds on these helpers."""
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): rendezvous, frame slicing / gathering of clip tensors, index helpers of the
+frame-sharded forward.  The forward's own exchanges do NOT go through torch.distributed: they are peer-memory kernels (p2p.py, csrc/fz_p2p.cu);
+`allreduce_set_sums` below is the reference semantics of the GroupNorm statistics exchange, kept for the CPU (gloo) tests."""
 from __future__ import annotations
 
 import os
