@@ -1,8 +1,9 @@
 """CPU fp32 restatement of the FateZero hot path (DDIM inversion + attention-fused denoising).  TEST INFRASTRUCTURE.
 
-Portable (plain torch on CPU, no /root/reference needed) so it travels to the GPU box as the parity checker for
-the CUDA path.  It is *pinned* against the unmodified reference run through oracle/ref_harness.py: see
-tests/test_oracle_pin.py (live, build container) and tests/golden/*.pt (committed vectors).
+Portable (plain torch, device-agnostic, no /root/reference needed) so it travels to the GPU box as the parity checker for
+the CUDA path.  It is *pinned* against the unmodified reference run through oracle/ref_harness.py (on a tests-only restatement of
+diffusers 0.11.1, oracle/shim/): oracle/make_golden.py writes tests/golden/*.pt in the build container and
+tests/test_oracle_golden.py holds this module to them.
 
 Every function cites the reference lines it restates (paths relative to /root/reference/video_diffusion):
   UNet forward ............ models/unet_3d_condition.py:307-446, models/unet_3d_blocks.py:208,303,401,508,606
