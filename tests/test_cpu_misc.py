@@ -209,3 +209,36 @@ def test_vae_spec_is_the_published_sd_vae():
     assert len(spec) == 248
     assert sum(int(torch.tensor(v).prod()) for v in spec.values()) == 83_653_863
     assert spec["encoder.mid_block.attentions.0.query.weight"] == (512, 512) and spec["quant_conv.weight"] == (8, 8, 1, 1)
+
+
+def test_disk_store_hands_out_paths_and_releases(tmp_path, monkeypatch):
+    """attention_store.py:103-106: with disk_store the per-step dict goes to a .pt file and the list holds its PATH (the maps are not kept)."""
+    from fatezero_b200 import controllers
+    monkeypatch.chdir(tmp_path)
+    s = controllers.AttentionStore(disk_store=True)
+    m = torch.rand(2, 8, 16, 80).half()
+    s.step_store["down_cross"].append(m[..., :77])
+    s.cur_step = 1
+    s.between_steps()
+    assert isinstance(s.attention_store_all_step[0], str) and s.attention_store_paths == s.attention_store_all_step
+    loaded = torch.load(s.attention_store_all_step[0])
+    assert torch.equal(loaded["down_cross"][0], m[..., :77]) and s.step_store == s.get_empty_store()
+    assert s.graph_signature() is None  # disk-backed stores always take the eager loops
+
+
+def test_controller_state_adoption():
+    """graphs.py: after a replay the caller's fresh controller adopts the captured controller's end-of-loop state (shallow list copies of
+    the same slabs), so mutating one object's lists never changes the other's."""
+    from fatezero_b200 import controllers
+    a, b = controllers.AttentionStore(), controllers.AttentionStore()
+    assert b.is_pristine() and b.graph_signature() == ("store", True, False)
+    a.cur_step = 3
+    a.attention_store_all_step = [{"down_cross": [torch.zeros(1)]}] * 3
+    a.latents_store = [torch.zeros(1)] * 3
+    a._acc = {"down_cross": [torch.ones(1)]}
+    a._graph_plan_id = 42
+    b.adopt_from(a)
+    assert b.cur_step == 3 and b._graph_plan_id == 42 and not b.is_pristine()
+    assert b.attention_store_all_step is not a.attention_store_all_step and b.attention_store_all_step[0] is a.attention_store_all_step[0]
+    b.latents_store.append(torch.zeros(1))
+    assert len(a.latents_store) == 3 and b._acc["down_cross"][0] is a._acc["down_cross"][0] and b._acc["down_cross"] is not a._acc["down_cross"]
