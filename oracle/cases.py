@@ -40,6 +40,12 @@ CASES = {
         frames=2, size=32, steps=3, source="a silver jeep driving down a curvy road", target="a silver tank driving down a curvy road",
         p2p=dict(is_replace_controller=True, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.6,
                  eq_params={"words": ["silver", "tank"], "values": [2.0, 4.0]})),
+    # BASELINE config #4 semantics (long clip, 'mid' source frame = frame 11 of 24, B*F = 48 rows in the CFG pass) at the mini geometry
+    "pin_long24": dict(
+        gpu=False, unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128),
+        frames=24, size=32, steps=2, source=SRC, target="watercolor painting of " + SRC,
+        p2p=dict(is_replace_controller=False, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.8,
+                 eq_params={"words": ["watercolor"], "values": [10, 10]})),
     # ---- SD-1.4 geometry (head dims 40/80/160): too slow for the CPU oracle inside the suites, so these goldens are compared with
     # the CUDA product directly (tests/test_gpu_golden_sd14.py); big=True -> make_golden keeps map slices + checksums only ----
     # BASELINE config #1: config/low_resource_teaser/jeep_watercolor_ddim_10_steps.yaml (Refine + Reweight x10, ['mid'] / 640)
