@@ -43,7 +43,7 @@ CASES = {
     # BASELINE config #4 semantics (long clip, 'mid' source frame = frame 11 of 24, B*F = 48 rows in the CFG pass) at the mini geometry
     "pin_long24": dict(
         gpu=False, unet="mini", model_config=dict(lora=160, SparseCausalAttention_index=["mid"], least_sc_channel=128),
-        frames=24, size=32, steps=2, source=SRC, target="watercolor painting of " + SRC,
+        frames=24, size=32, steps=1, source=SRC, target="watercolor painting of " + SRC,
         p2p=dict(is_replace_controller=False, cross_replace_steps={"default_": 0.8}, self_replace_steps=0.8,
                  eq_params={"words": ["watercolor"], "values": [10, 10]})),
     # ---- SD-1.4 geometry (head dims 40/80/160): too slow for the CPU oracle inside the suites, so these goldens are compared with
